@@ -1,0 +1,69 @@
+"""Build libdmp2.so (all CUDA kernels + the C ABI) for sm_100a with nvcc, in-tree.
+
+    python -m dmpfold2_b200.build [--force]
+
+nvcc cross-compiles without a GPU; the .so travels to the GPU box with the repo snapshot.
+"""
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+OBJ = os.path.join(HERE, 'build')
+LIB = os.path.join(HERE, 'libdmp2.so')
+SOURCES = ['engine.cu', 'msa.cu', 'gru.cu', 'resnet.cu', 'conv_tc.cu', 'eig.cu', 'geom.cu']
+NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-Xcompiler', '-fPIC',
+         '--expt-relaxed-constexpr', '-Xptxas', '-v']
+
+
+def _deps():
+    return [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, '..', 'include', 'dmp2.h')]
+
+
+def _stale(target, deps):
+    if not os.path.isfile(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    os.makedirs(OBJ, exist_ok=True)
+    deps = _deps()
+    jobs = []
+    for src in SOURCES:
+        obj = os.path.join(OBJ, src.replace('.cu', '.o'))
+        if force or _stale(obj, deps):
+            jobs.append((src, obj))
+
+    def compile_one(job):
+        src, obj = job
+        cmd = [NVCC] + FLAGS + ['-c', os.path.join(CSRC, src), '-o', obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        return src, r
+
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        for src, r in ex.map(compile_one, jobs):
+            log = os.path.join(OBJ, src.replace('.cu', '.ptxas.log'))
+            with open(log, 'w') as fh:
+                fh.write(r.stderr)
+            if r.returncode != 0:
+                sys.stderr.write(r.stdout + r.stderr)
+                raise RuntimeError(f'nvcc failed on {src}')
+            if verbose:
+                sys.stderr.write(r.stderr)
+    objs = [os.path.join(OBJ, s.replace('.cu', '.o')) for s in SOURCES]
+    if force or jobs or _stale(LIB, objs):
+        cmd = [NVCC, '-shared', '-o', LIB] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a', '-lcudart']
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError('link failed')
+    return LIB
+
+
+if __name__ == '__main__':
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

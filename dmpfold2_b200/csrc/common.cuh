@@ -1,0 +1,204 @@
+// Shared declarations for libdmp2.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include <map>
+
+#include "../../include/dmp2.h"
+
+#define DMP2_CH 128          // ResNet width (network.py: GRUResNet(512,128))
+#define DMP2_W 512           // GRU width
+#define DMP2_NBLOCKS 16
+#define DMP2_FEAT_LD 444     // 441 DCA + 1 APC + 2 zero pad (float4-aligned rows)
+#define DMP2_STEM_K (512 + DMP2_FEAT_LD)
+
+struct Launch {              // per-engine launch bookkeeping (gpu_launches) + sticky error
+    int64_t count = 0;
+    std::string err;
+    int status = 0;
+};
+
+#define CUDA_TRY(e, call)                                                                                   \
+    do {                                                                                                    \
+        cudaError_t _c = (call);                                                                            \
+        if (_c != cudaSuccess) {                                                                            \
+            return (e)->fail(_c == cudaErrorMemoryAllocation ? DMP2_ERR_OOM : DMP2_ERR_CUDA,                \
+                             std::string(#call) + ": " + cudaGetErrorString(_c));                           \
+        }                                                                                                   \
+    } while (0)
+
+// After every kernel launch: count it and catch launch-configuration errors immediately.
+#define POST_LAUNCH(e, name)                                                                                \
+    do {                                                                                                    \
+        (e)->launches++;                                                                                    \
+        cudaError_t _c = cudaGetLastError();                                                                \
+        if (_c != cudaSuccess) return (e)->fail(DMP2_ERR_CUDA, std::string(name) + ": " + cudaGetErrorString(_c)); \
+    } while (0)
+
+#define TRY(x)                                                                                              \
+    do {                                                                                                    \
+        int _s = (x);                                                                                       \
+        if (_s != 0) return _s;                                                                             \
+    } while (0)
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------------------------------------------
+// Repacked weights (device).  Layouts are documented in DESIGN.md "Data layout in HBM".
+// ---------------------------------------------------------------------------------------------------
+struct GruDir {              // one direction of one layer of a hidden-256 bidirectional GRU
+    float* w_hh;             // [768][256] as in the state_dict (gate order r,z,n)
+    float* b_hh;             // [768]
+};
+struct BiGruLayer {
+    float* w_ih;             // [1536][K] : rows 0..767 forward, 768..1535 reverse  (K = input width, mult of 4)
+    float* b_ih;             // [1536]
+    int K;
+    GruDir dir[2];
+};
+
+struct ResBlockW {
+    float* w_f32;            // [512][25][128]  (cout, tap=ky*5+kx, cin)  fp32, for the FFMA path
+    __half* w_hi;            // same layout, fp16 high part
+    __half* w_lo;            // fp16 residual  (w - float(w_hi))
+    float* bias;             // [512]
+    float* gamma;            // [128]
+    float* beta;             // [128]
+    float* gate_c;           // [128]  cSE gate, a weights-only constant: sigmoid(W2 relu(W1 beta))
+    float* sse_w;            // [128]
+    float sse_b;
+};
+
+struct Weights {
+    // vgru (network.py:189): packed so that one GEMM row-quad yields all gates of a hidden unit
+    float* vg_gi0;           // [22][512][4]   W_ih_l0 column gather + b_ih (r, z, n, 0)
+    float* vg_w0;            // [2048][512]    rows 4j+{0,1,2}: W_hh_l0 rows {j,512+j,1024+j}; 4j+3: 0
+    float* vg_b0;            // [2048]         b_hh_l0 in the same order
+    float* vg_w1;            // [2048][1024]   4j+0/1: [W_ih_l1 | W_hh_l1] (r,z); 4j+2: [W_ih_n | 0]; 4j+3: [0 | W_hh_n]
+    float* vg_b1;            // [2048]         (b_ih_r+b_hh_r, b_ih_z+b_hh_z, b_ih_n, b_hh_n)
+    BiGruLayer hgru[2];
+    BiGruLayer cgru[3];
+    float* coord_fc;         // [3][512]
+    float* stem_w;           // [384][DMP2_STEM_K]  cols 0..511 outer, 512..953 DCA+APC, pad 0
+    float* stem_b;           // [384]
+    float* stem_wd;          // [384]  weight of input channel 954 (the recycled distance map)
+    float* stem_gamma;       // [128]
+    float* stem_beta;        // [128]
+    ResBlockW blk[DMP2_NBLOCKS];
+    float* head_w;           // [2][128]
+    float head_b[2];
+};
+
+// ---------------------------------------------------------------------------------------------------
+// Workspace (device), sized for (L, N); grown on demand.
+// ---------------------------------------------------------------------------------------------------
+struct Workspace {
+    int L = 0, N = 0;
+    // MSA features
+    uint8_t* msa = nullptr;        // [N][L] codes (engine-owned copy for the host entry point)
+    uint8_t* msa_t = nullptr;      // [L][Npad4] clamped codes, column-major for coalesced identity counts
+    float* seqw = nullptr;         // [N]
+    float* scal = nullptr;         // [8] scalars: sum w, n_eff, ridge, ...
+    float* xc = nullptr;           // [21L][Npad4] centred, sqrt(w)-scaled one-hot, transposed (K = sequence axis)
+    float* cov = nullptr;          // [npad][npad] covariance -> inverse in place
+    float* gj_p = nullptr;         // [64][64] pivot inverse
+    float* gj_r = nullptr;         // [64][npad] row panel
+    float* x3 = nullptr;           // [L][L] contact norms
+    float* apc = nullptr;          // [2L+1] row sums, col sums, total
+    float* feat = nullptr;         // [L*L][444]
+    // 1-D track
+    float* vg_h = nullptr;         // [2 layers][2 buffers][L][512]
+    float* v_last = nullptr;       // [L][512]
+    float* gi = nullptr;           // [L][1536] input projections of the current bi-GRU layer
+    float* seq_a = nullptr;        // [L][520] layer input / output ping
+    float* seq_b = nullptr;        // [L][512] pong
+    float* mat1d_t = nullptr;      // [L][512] hgru output (time-major == mat1d transposed)
+    // 2-D track
+    float* dmap = nullptr;         // [L*L]
+    float* base384 = nullptr;      // [L*L][384] cached stem pre-activation without the dmap term
+    float* raw = nullptr;          // [L*L][128] maxout output before InstanceNorm
+    float* x = nullptr;            // [L*L][128] residual stream fp32 (NHWC)
+    __half* xh = nullptr;          // [L*L][128] fp16 high part of x
+    __half* xl = nullptr;          // [L*L][128] fp16 low part
+    double* stat_part = nullptr;   // [nparts][256] partial sums
+    float* norm_ss = nullptr;      // [256] per-channel scale, shift
+    unsigned int* ticket = nullptr;
+    float* head = nullptr;         // [2][L*L]
+    float* conf = nullptr;         // [L]
+    float* mmat = nullptr;         // [L*L]
+    double* eig_a = nullptr;       // [L*L] working matrix (fp64)
+    double* eig_w = nullptr;       // small vectors: d, e, beta, z[8][L], ...
+    float* eig_val = nullptr;      // [8]
+    float* mds = nullptr;          // [L][8]
+    float* ca = nullptr;           // [L][3]
+    float* best_ca = nullptr;      // [L][3]
+    float* best_conf = nullptr;    // [L]
+    float* best_mean = nullptr;    // [1]
+    float* coords_out = nullptr;   // [L][5][3]
+    float* conf_out = nullptr;     // [L]
+    std::vector<void*> allocs;
+};
+
+struct dmp2_engine {
+    int device = 0;
+    int num_sms = 148;
+    int conv_mode = DMP2_CONV_TC_F16X3;
+    int64_t launches = 0;
+    int status = 0;
+    std::string err;
+    Weights w;
+    std::vector<void*> weight_allocs;
+    Workspace ws;
+    cudaEvent_t ev[16];
+    bool ev_ok = false;
+    float stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    void* tc_state = nullptr;        // tensor-core conv state (tensor maps), owned by conv_tc.cu
+
+    int fail(int code, const std::string& msg) {
+        status = code;
+        err = msg;
+        return code;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// Stage launchers (one per .cu file).  All asynchronous on `st`.
+// ---------------------------------------------------------------------------------------------------
+// msa.cu
+int run_reweight(dmp2_engine* e, const uint8_t* msa, int N, int L, float* w_out, cudaStream_t st);
+int run_dca(dmp2_engine* e, const uint8_t* msa, int N, int L, const float* w, float* feat444, cudaStream_t st);
+int run_feat_export(dmp2_engine* e, const float* feat444, int L, float* feat442, cudaStream_t st);
+int run_feat_import(dmp2_engine* e, const float* feat442, int L, float* feat444, cudaStream_t st);
+// gru.cu
+int run_vgru(dmp2_engine* e, const uint8_t* msa, int N, int L, float* out, cudaStream_t st);
+int run_bigru(dmp2_engine* e, const BiGruLayer* layers, int nlayers, const float* in, int L, float* out, cudaStream_t st);
+int run_coord_head(dmp2_engine* e, const float* mat1d_t, const float* mds, int L, float* ca, cudaStream_t st);
+// resnet.cu
+int run_stem_base(dmp2_engine* e, const float* mat1d_t, const float* feat444, int L, cudaStream_t st);
+int run_stem_update(dmp2_engine* e, const float* dmap, int L, cudaStream_t st);   // -> ws.x (+ xh, xl)
+int run_conv_ffma(dmp2_engine* e, int blk, const float* x, int L, float* raw, cudaStream_t st);
+int run_norm_gate(dmp2_engine* e, int blk, const float* raw, float* x, int L, bool stem, cudaStream_t st);
+int run_split_half(dmp2_engine* e, const float* x, int64_t n, __half* hi, __half* lo, cudaStream_t st);
+int run_resblock(dmp2_engine* e, int blk, int L, cudaStream_t st);                // ws.x -> ws.x
+int run_head(dmp2_engine* e, const float* x, int L, float* head2, cudaStream_t st);
+int run_head_post(dmp2_engine* e, const float* head2, int L, float* conf, float* mmat, cudaStream_t st);
+// conv_tc.cu
+int run_conv_tc(dmp2_engine* e, int blk, const __half* xh, const __half* xl, int L, float* raw, int mode, cudaStream_t st);
+int run_gemm_tn_test(dmp2_engine* e, const float* a, const float* b, int M, int N, int K, int mode, float* c, cudaStream_t st);
+void conv_tc_destroy(dmp2_engine* e);
+// eig.cu
+int run_eig_top8(dmp2_engine* e, const float* m, int L, float* vals, float* mds_scaled, float* vecs_raw, cudaStream_t st);
+// geom.cu
+int run_dmap(dmp2_engine* e, const float* ca, int L, float* dmap, bool clamp, cudaStream_t st);
+int run_fill(dmp2_engine* e, float* p, int64_t n, float v, cudaStream_t st);
+int run_refine(dmp2_engine* e, float* ca, int L, int steps, cudaStream_t st);
+int run_backbone(dmp2_engine* e, const float* ca, const float* conf_logit, int L, float* out, float* conf_out, cudaStream_t st);
+int run_select(dmp2_engine* e, const float* ca, const float* conf, int L, int first, cudaStream_t st);
+
+// workspace
+int ensure_workspace(dmp2_engine* e, int L, int N);

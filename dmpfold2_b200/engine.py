@@ -1,0 +1,261 @@
+"""ctypes binding of libdmp2.so (include/dmp2.h) -- the only way the Python host reaches the GPU kernels.
+
+There is no CPU fallback and no PyTorch implementation of any stage in this package: if the library is not
+built (python -m dmpfold2_b200.build) or no sm_100 device is present, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libdmp2.so')
+
+CONV_TC_F16X3, CONV_TC_F16, CONV_FFMA = 0, 1, 2
+CONV_MODES = {'f16x3': CONV_TC_F16X3, 'f16': CONV_TC_F16, 'ffma': CONV_FFMA}
+STAGE_NAMES = ('msa_features', 'vgru', 'hgru', 'stem_base', 'recycling_passes', 'final_refine_backbone')
+
+_lib = None
+
+_vp, _i, _i64 = C.c_void_p, C.c_int, C.c_int64
+_SIGS = {
+    'dmp2_create': (_i, [C.POINTER(_vp), _i, _i, C.POINTER(C.c_char_p), C.POINTER(_vp), C.POINTER(_i64)]),
+    'dmp2_destroy': (None, [_vp]),
+    'dmp2_last_error': (C.c_char_p, [_vp]),
+    'dmp2_set_conv_mode': (_i, [_vp, _i]),
+    'dmp2_launch_count': (_i64, [_vp]),
+    'dmp2_stage_times': (_i, [_vp, C.POINTER(C.c_float), _i]),
+    'dmp2_fold': (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp]),
+    'dmp2_fold_host': (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _vp]),
+    'dmp2_reweight': (_i, [_vp, _vp, _i, _i, _vp, _vp]),
+    'dmp2_dca': (_i, [_vp, _vp, _i, _i, _vp, _vp]),
+    'dmp2_vgru': (_i, [_vp, _vp, _i, _i, _vp, _vp]),
+    'dmp2_hgru': (_i, [_vp, _vp, _i, _vp, _vp]),
+    'dmp2_conv5_maxout': (_i, [_vp, _i, _vp, _i, _vp, _vp]),
+    'dmp2_resblock': (_i, [_vp, _i, _vp, _i, _vp, _vp]),
+    'dmp2_resnet_pass': (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    'dmp2_head_mds': (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    'dmp2_eig_top8': (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
+    'dmp2_coord_gru': (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
+    'dmp2_refine': (_i, [_vp, _vp, _i, _i, _vp]),
+    'dmp2_backbone': (_i, [_vp, _vp, _i, _vp, _vp]),
+    'dmp2_gemm_tn_test': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+}
+EXPORTS = tuple(_SIGS)
+
+
+def load_library() -> C.CDLL:
+    """dlopen libdmp2.so and type every export of include/dmp2.h.  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(f'{LIB_PATH} is missing: build it with `python -m dmpfold2_b200.build` '
+                               '(this engine has no CPU or PyTorch fallback)')
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+class Dmp2Error(RuntimeError):
+    pass
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class Engine:
+    """One engine per (device, stream): owns the repacked weights and the workspace on that device."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device_index: int = 0, conv_mode: Optional[str] = None):
+        self.lib = load_library()
+        if not torch.cuda.is_available():
+            raise Dmp2Error('no CUDA device visible: the DMPfold2 B200 engine has no CPU fallback')
+        self.device_index = int(device_index)
+        self.device = torch.device('cuda', self.device_index)
+        keep = [(k, v.detach().to('cpu', torch.float32).contiguous()) for k, v in state_dict.items()]
+        n = len(keep)
+        names = (C.c_char_p * n)(*[k.encode() for k, _ in keep])
+        ptrs = (C.c_void_p * n)(*[v.data_ptr() for _, v in keep])
+        numels = (C.c_int64 * n)(*[v.numel() for _, v in keep])
+        handle = C.c_void_p()
+        st = self.lib.dmp2_create(C.byref(handle), self.device_index, n, names, ptrs, numels)
+        if st != 0:
+            raise Dmp2Error(f'dmp2_create failed ({st}): {self.lib.dmp2_last_error(None).decode()}')
+        self.h = handle
+        if conv_mode is not None:
+            self.set_conv_mode(conv_mode)
+
+    def close(self):
+        if getattr(self, 'h', None):
+            self.lib.dmp2_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------
+    def _check(self, st: int, what: str):
+        if st != 0:
+            raise Dmp2Error(f'{what} failed ({st}): {self.lib.dmp2_last_error(self.h).decode()}')
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _dev(self, a, dtype) -> torch.Tensor:
+        t = torch.as_tensor(a)
+        return t.to(self.device, dtype).contiguous()
+
+    def _empty(self, *shape) -> torch.Tensor:
+        return torch.empty(shape, dtype=torch.float32, device=self.device)
+
+    def set_conv_mode(self, mode):
+        m = CONV_MODES[mode] if isinstance(mode, str) else int(mode)
+        self._check(self.lib.dmp2_set_conv_mode(self.h, m), 'dmp2_set_conv_mode')
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.dmp2_launch_count(self.h))
+
+    def stage_times(self) -> Dict[str, float]:
+        buf = (C.c_float * 8)()
+        n = self.lib.dmp2_stage_times(self.h, buf, 8)
+        return {STAGE_NAMES[i]: float(buf[i]) for i in range(n)}
+
+    # ---- the hot path --------------------------------------------------------------------------
+    def fold(self, msa: torch.Tensor, template_ca: Optional[torch.Tensor] = None, iterations: int = 10,
+             minsteps: int = 100) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Device tensors in, device tensors out; asynchronous on the current torch stream.
+        msa uint8 (N,L) codes 0..21; template_ca float32 (L,3) or None -> coords (L,5,3), confs (L,)."""
+        msa = self._dev(msa, torch.uint8)
+        n, l = msa.shape
+        tm = None
+        if template_ca is not None:
+            tm = self._dev(template_ca, torch.float32)
+            if tuple(tm.shape) != (l, 3):
+                raise ValueError(f'template has {tm.shape[0]} CA atoms, alignment has {l} columns')
+        coords, conf = self._empty(l, 5, 3), self._empty(l)
+        with torch.cuda.device(self.device):
+            st = self.lib.dmp2_fold(self.h, _ptr(msa), n, l, _ptr(tm), int(iterations), int(minsteps), _ptr(coords),
+                                    _ptr(conf), self._stream())
+        self._check(st, 'dmp2_fold')
+        return coords, conf
+
+    def fold_host(self, msa: np.ndarray, template_ca: Optional[np.ndarray] = None, iterations: int = 10,
+                  minsteps: int = 100) -> Tuple[np.ndarray, np.ndarray]:
+        """Host buffers in/out through dmp2_fold_host (H2D + fold + D2H + sync) -- the end-to-end call."""
+        msa = np.ascontiguousarray(msa, dtype=np.uint8)
+        n, l = msa.shape
+        tm = None if template_ca is None else np.ascontiguousarray(template_ca, dtype=np.float32)
+        coords = np.empty((l, 5, 3), dtype=np.float32)
+        conf = np.empty((l,), dtype=np.float32)
+        st = self.lib.dmp2_fold_host(self.h, msa.ctypes.data_as(C.c_void_p), n, l,
+                                     None if tm is None else tm.ctypes.data_as(C.c_void_p), int(iterations), int(minsteps),
+                                     coords.ctypes.data_as(C.c_void_p), conf.ctypes.data_as(C.c_void_p))
+        self._check(st, 'dmp2_fold_host')
+        return coords, conf
+
+    # ---- stage entry points (parity tests) -------------------------------------------------------
+    def reweight(self, msa) -> torch.Tensor:
+        msa = self._dev(msa, torch.uint8)
+        n, l = msa.shape
+        out = self._empty(n)
+        self._check(self.lib.dmp2_reweight(self.h, _ptr(msa), n, l, _ptr(out), self._stream()), 'dmp2_reweight')
+        return out
+
+    def dca(self, msa) -> torch.Tensor:
+        msa = self._dev(msa, torch.uint8)
+        n, l = msa.shape
+        out = self._empty(l, l, 442)
+        self._check(self.lib.dmp2_dca(self.h, _ptr(msa), n, l, _ptr(out), self._stream()), 'dmp2_dca')
+        return out
+
+    def vgru(self, msa) -> torch.Tensor:
+        msa = self._dev(msa, torch.uint8)
+        n, l = msa.shape
+        out = self._empty(l, 512)
+        self._check(self.lib.dmp2_vgru(self.h, _ptr(msa), n, l, _ptr(out), self._stream()), 'dmp2_vgru')
+        return out
+
+    def hgru(self, x) -> torch.Tensor:
+        x = self._dev(x, torch.float32)
+        out = self._empty(x.shape[0], 512)
+        self._check(self.lib.dmp2_hgru(self.h, _ptr(x), x.shape[0], _ptr(out), self._stream()), 'dmp2_hgru')
+        return out
+
+    def conv5_maxout(self, block: int, x_nhwc) -> torch.Tensor:
+        x = self._dev(x_nhwc, torch.float32)
+        l = x.shape[0]
+        out = self._empty(l, l, 128)
+        self._check(self.lib.dmp2_conv5_maxout(self.h, block, _ptr(x), l, _ptr(out), self._stream()), 'dmp2_conv5_maxout')
+        return out
+
+    def resblock(self, block: int, x_nhwc) -> torch.Tensor:
+        x = self._dev(x_nhwc, torch.float32)
+        l = x.shape[0]
+        out = self._empty(l, l, 128)
+        self._check(self.lib.dmp2_resblock(self.h, block, _ptr(x), l, _ptr(out), self._stream()), 'dmp2_resblock')
+        return out
+
+    def resnet_pass(self, mat1d_t, feat, dmap) -> torch.Tensor:
+        m = self._dev(mat1d_t, torch.float32)
+        f = self._dev(feat, torch.float32)
+        d = self._dev(dmap, torch.float32)
+        l = m.shape[0]
+        out = self._empty(2, l, l)
+        self._check(self.lib.dmp2_resnet_pass(self.h, _ptr(m), _ptr(f), _ptr(d), l, _ptr(out), self._stream()),
+                    'dmp2_resnet_pass')
+        return out
+
+    def head_mds(self, head):
+        h = self._dev(head, torch.float32)
+        l = h.shape[-1]
+        conf, m, mds = self._empty(l), self._empty(l, l), self._empty(l, 8)
+        self._check(self.lib.dmp2_head_mds(self.h, _ptr(h), l, _ptr(conf), _ptr(m), _ptr(mds), self._stream()), 'dmp2_head_mds')
+        return conf, m, mds
+
+    def eig_top8(self, m):
+        m = self._dev(m, torch.float32)
+        l = m.shape[0]
+        vals, vecs = self._empty(8), self._empty(l, 8)
+        self._check(self.lib.dmp2_eig_top8(self.h, _ptr(m), l, _ptr(vals), _ptr(vecs), self._stream()), 'dmp2_eig_top8')
+        return vals, vecs
+
+    def coord_gru(self, mat1d_t, mds) -> torch.Tensor:
+        m = self._dev(mat1d_t, torch.float32)
+        d = self._dev(mds, torch.float32)
+        l = m.shape[0]
+        out = self._empty(l, 3)
+        self._check(self.lib.dmp2_coord_gru(self.h, _ptr(m), _ptr(d), l, _ptr(out), self._stream()), 'dmp2_coord_gru')
+        return out
+
+    def refine(self, ca, steps: int) -> torch.Tensor:
+        c = self._dev(ca, torch.float32).clone()
+        self._check(self.lib.dmp2_refine(self.h, _ptr(c), c.shape[0], int(steps), self._stream()), 'dmp2_refine')
+        return c
+
+    def backbone(self, ca) -> torch.Tensor:
+        c = self._dev(ca, torch.float32)
+        out = self._empty(c.shape[0], 5, 3)
+        self._check(self.lib.dmp2_backbone(self.h, _ptr(c), c.shape[0], _ptr(out), self._stream()), 'dmp2_backbone')
+        return out
+
+    def gemm_tn_test(self, a, b, mode='f16x3') -> torch.Tensor:
+        a = self._dev(a, torch.float32)
+        b = self._dev(b, torch.float32)
+        m, k = a.shape
+        n = b.shape[0]
+        out = self._empty(m, n)
+        self._check(self.lib.dmp2_gemm_tn_test(self.h, _ptr(a), _ptr(b), m, n, k, CONV_MODES[mode], _ptr(out), self._stream()),
+                    'dmp2_gemm_tn_test')
+        return out

@@ -1,0 +1,118 @@
+/*
+ * dmp2.h -- C ABI of libdmp2.so, the B200-native (sm_100a) DMPfold2 inference engine.
+ *
+ * The reference (psipred/DMPfold2) has no FFI/plugin layer: its boundary is the Python call
+ *     network(inputs, inputs2, nloops, refine_steps)            dmpfold/predict.py:151, network.py:218
+ * made by aln_to_coords()                                       dmpfold/predict.py:74-158
+ * plus the state_dict key/shape schema it loads                 dmpfold/predict.py:83-98.
+ * This header is what a ctypes binding on the reference side would bind instead of that call; see
+ * INTEGRATION.md for the stub.  Plain pointers and sizes only; no torch types.
+ *
+ * Conventions
+ *   - every entry point returns 0 on success or a negative dmp2_status; nothing throws across the ABI;
+ *     dmp2_last_error() gives the message for the last failure on that engine (or the global one for
+ *     dmp2_create failures when engine == NULL).
+ *   - "dev" pointers are device memory on the engine's CUDA device, "host" pointers are CPU memory.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  Entry points that
+ *     take device pointers are asynchronous on that stream and never synchronise the host; the caller
+ *     keeps the buffers alive until the stream is synchronised.
+ *   - an engine is bound to one device and is not re-entrant: one engine per (device, stream).
+ */
+#ifndef DMP2_H
+#define DMP2_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dmp2_engine dmp2_engine;
+
+typedef enum {
+    DMP2_OK = 0,
+    DMP2_ERR_BAD_ARG = -1,        /* NULL pointer, L < 8, N < 1, negative counts ...            */
+    DMP2_ERR_MISSING_WEIGHT = -2, /* a state_dict key of predict.py:98 is absent or mis-sized   */
+    DMP2_ERR_CUDA = -3,           /* a CUDA runtime/driver call or kernel launch failed         */
+    DMP2_ERR_OOM = -4,            /* device allocation failed                                   */
+    DMP2_ERR_NO_DEVICE = -5,      /* no usable sm_100 device: there is NO CPU fallback          */
+    DMP2_ERR_UNSUPPORTED = -6
+} dmp2_status;
+
+/* Convolution arithmetic of the sixteen 5x5 ResNet blocks (network.py:26 inside ResNet_Block). */
+typedef enum {
+    DMP2_CONV_TC_F16X3 = 0, /* tcgen05, fp16 hi+lo split of both operands, 3 MMAs, fp32 accumulate (parity mode) */
+    DMP2_CONV_TC_F16 = 1,   /* tcgen05, single fp16 MMA, fp32 accumulate (fast mode; ~1e-3 A drift)              */
+    DMP2_CONV_FFMA = 2      /* CUDA-core fp32 implicit GEMM (validation path for the tensor-core kernels)        */
+} dmp2_conv_mode;
+
+/* ---- lifetime ------------------------------------------------------------------------------------ */
+
+/* Build an engine on CUDA device `device` from the reference's state_dict (predict.py:89-98): `names[i]`
+ * is the state_dict key, `host_ptrs[i]` a contiguous fp32 host array of `numels[i]` elements.  All 184
+ * keys of the published model are required (strict, like load_state_dict).  The engine uploads and
+ * repacks the weights into its own layouts and owns the copies. */
+int dmp2_create(dmp2_engine** out, int device, int n_tensors, const char* const* names,
+                const float* const* host_ptrs, const int64_t* numels);
+void dmp2_destroy(dmp2_engine* e);
+const char* dmp2_last_error(const dmp2_engine* e);
+int dmp2_set_conv_mode(dmp2_engine* e, int mode /* dmp2_conv_mode */);
+/* Number of this library's kernels launched by the engine since creation (bench.py's gpu_launches). */
+int64_t dmp2_launch_count(const dmp2_engine* e);
+/* Per-stage device time of the last dmp2_fold_host call, in ms (CUDA events): out[0..n) in the order
+ * features, vgru, hgru, stem, resnet(conv+norm), head+eig, coord_gru, refine+backbone.  Returns n. */
+int dmp2_stage_times(const dmp2_engine* e, float* out_ms, int cap);
+
+/* ---- the hot path: replaces network(inputs, inputs2, nloops, refine_steps) + predict.py:136-147 ---- */
+
+/* msa_dev: uint8 N x L row-major residue codes 0..21 as produced by predict.py:124-128 (row 0 = query).
+ * tmpl_ca_dev: L x 3 template CA coordinates (predict.py:106-119) or NULL (dmap channel = -1).
+ * coords_out_dev: L x 5 x 3 fp32 (N, CA, C, O, CB per residue; predict.py:152); conf_out_dev: L fp32. */
+int dmp2_fold(dmp2_engine* e, const uint8_t* msa_dev, int N, int L, const float* tmpl_ca_dev, int iterations,
+              int minsteps, float* coords_out_dev, float* conf_out_dev, void* stream);
+
+/* Same with HOST buffers: copies the alignment up, runs the fold, copies coords/conf back and
+ * synchronises.  This is the call timed as the end-to-end number. */
+int dmp2_fold_host(dmp2_engine* e, const uint8_t* msa_host, int N, int L, const float* tmpl_ca_host, int iterations,
+                   int minsteps, float* coords_out_host, float* conf_out_host);
+
+/* ---- stage entry points (teacher-forced parity tests; all device pointers, async on `stream`) ------ */
+
+/* predict.py:32-37  reweight: w (N) */
+int dmp2_reweight(dmp2_engine* e, const uint8_t* msa_dev, int N, int L, float* w_out_dev, void* stream);
+/* predict.py:41-61  fast_dca: feat (L, L, 442) row-major exactly like the reference tensor */
+int dmp2_dca(dmp2_engine* e, const uint8_t* msa_dev, int N, int L, float* feat_out_dev, void* stream);
+/* network.py:223-225  embed + vgru: final hidden state per column, (L, 512) */
+int dmp2_vgru(dmp2_engine* e, const uint8_t* msa_dev, int N, int L, float* out_dev, void* stream);
+/* network.py:225-226  hgru: in (L, 512) -> out (L, 512) [fwd | bwd] */
+int dmp2_hgru(dmp2_engine* e, const float* in_dev, int L, float* out_dev, void* stream);
+/* network.py:26 + :30-31 of block `block` (1..16): x (L*L, 128) NHWC fp32 -> max over 4 consecutive conv
+ * channels of (conv5x5 + bias), (L*L, 128) NHWC fp32, before the InstanceNorm. */
+int dmp2_conv5_maxout(dmp2_engine* e, int block, const float* x_nhwc_dev, int L, float* out_nhwc_dev, void* stream);
+/* network.py:94-103  one full ResNet_Block: x (L*L,128) NHWC -> (L*L,128) NHWC */
+int dmp2_resblock(dmp2_engine* e, int block, const float* x_nhwc_dev, int L, float* out_nhwc_dev, void* stream);
+/* network.py:229-235  one ResNet pass from its inputs: mat1d_t (L,512) time-major hgru output, feat (L,L,442),
+ * dmap (L,L) -> head (2, L, L) like resnet.17's output. */
+int dmp2_resnet_pass(dmp2_engine* e, const float* mat1d_t_dev, const float* feat_dev, const float* dmap_dev, int L,
+                     float* head_out_dev, void* stream);
+/* network.py:237-250  head (2,L,L) -> conf (L), M (L,L), mds (L,8) (ascending eigenvalue order, canonical sign) */
+int dmp2_head_mds(dmp2_engine* e, const float* head_dev, int L, float* conf_out_dev, float* m_out_dev,
+                  float* mds_out_dev, void* stream);
+/* top-8 eigenpairs of a symmetric L x L fp32 matrix: vals (8) ascending, vecs (L,8), canonical sign */
+int dmp2_eig_top8(dmp2_engine* e, const float* m_dev, int L, float* vals_out_dev, float* vecs_out_dev, void* stream);
+/* network.py:251-255  coord_gru + coord_fc: mat1d_t (L,512), mds (L,8) -> CA (L,3) */
+int dmp2_coord_gru(dmp2_engine* e, const float* mat1d_t_dev, const float* mds_dev, int L, float* ca_out_dev, void* stream);
+/* network.py:106-137  refine_coords, in place on ca (L,3) */
+int dmp2_refine(dmp2_engine* e, float* ca_dev, int L, int steps, void* stream);
+/* network.py:141-177  calpha_to_main_chain: ca (L,3) -> (L,5,3) */
+int dmp2_backbone(dmp2_engine* e, const float* ca_dev, int L, float* out_dev, void* stream);
+
+/* Generic fp32 GEMM self-test hook for the tensor-core GEMM core: C[M,N] = A[M,K] * B[N,K]^T through the
+ * same tcgen05 pipeline the conv uses (mode as dmp2_conv_mode).  K % 64 == 0. */
+int dmp2_gemm_tn_test(dmp2_engine* e, const float* a_dev, const float* b_dev, int M, int N, int K, int mode,
+                      float* c_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMP2_H */

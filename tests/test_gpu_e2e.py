@@ -1,0 +1,98 @@
+"""GPU end-to-end parity: the whole fold against the golden vectors the reference produced (oracle B) and
+against the oracle at other sizes.  Bar: CA-RMSD <= 1e-3 A (BASELINE.json north_star), atom order N,CA,C,O,CB."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, ROOT, needs_weights
+from oracle import dmpfold_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL_RMSD = 1e-3          # Angstrom, the north_star tolerance
+
+
+@pytest.fixture(scope='module')
+def eng(state_dict):
+    from dmpfold2_b200.engine import Engine
+    e = Engine(state_dict, 0)
+    yield e
+    e.close()
+
+
+def _check(coords, conf, g, tol=TOL_RMSD):
+    coords, conf = np.asarray(coords), np.asarray(conf)
+    assert coords.shape == g['coords'].shape and np.isfinite(coords).all()
+    rmsd = O.kabsch_rmsd(coords[:, 1], g['coords'][:, 1])
+    rmsd_all = O.kabsch_rmsd(coords.reshape(-1, 3), g['coords'].reshape(-1, 3))
+    assert rmsd <= tol and rmsd_all <= 2 * tol, (rmsd, rmsd_all)
+    assert np.abs(conf - g['confs']).max() < 2e-3
+    return rmsd
+
+
+@needs_weights
+@pytest.mark.parametrize('mode', ['ffma', 'f16x3'])
+@pytest.mark.parametrize('n,m', [(0, 0), (2, 20), (10, 100)])
+def test_pf10963_matches_reference(eng, pf10963, mode, n, m):
+    g = np.load(os.path.join(GOLDEN, f'pf10963_n{n}_m{m}.npz'))
+    eng.set_conv_mode(mode)
+    coords, conf = eng.fold(torch.from_numpy(pf10963), None, n, m)
+    _check(coords.cpu().numpy(), conf.cpu().numpy(), g)
+    c2, f2 = eng.fold_host(pf10963, None, n, m)                    # host-buffer entry point, same result
+    assert np.array_equal(c2, coords.cpu().numpy()) and np.array_equal(f2, conf.cpu().numpy())
+
+
+@needs_weights
+def test_template_and_single_sequence(eng, pf10963, tmp_path):
+    eng.set_conv_mode('f16x3')
+    g = np.load(os.path.join(GOLDEN, 'pf10963_tmpl_n1_m10.npz'))
+    pdb = tmp_path / 't.pdb'
+    pdb.write_text(str(g['pdb_text']))
+    ca = O.read_template_ca(str(pdb))
+    coords, conf = eng.fold_host(pf10963, ca, 1, 10)
+    _check(coords, conf, g)
+    g1 = np.load(os.path.join(GOLDEN, 'pf10963_single_n1_m0.npz'))
+    coords, conf = eng.fold_host(pf10963[:1], None, 1, 0)
+    _check(coords, conf, g1)
+
+
+@pytest.mark.parametrize('l,n,seed', [(57, 40, 1), (164, 96, 2)])
+def test_structured_synthetic_vs_oracle(eng, oracle, pf10963, l, n, seed):
+    msa = O.synth_msa_structured(pf10963, l, n, seed)
+    ref_c, ref_f = oracle.fold(msa, iterations=1, minsteps=10)
+    eng.set_conv_mode('f16x3')
+    coords, conf = eng.fold_host(msa, None, 1, 10)
+    _check(coords, conf, {'coords': ref_c.numpy(), 'confs': ref_f.numpy()})
+
+
+@needs_weights
+def test_fold_is_deterministic_and_negative_counts_clamp(eng, pf10963):
+    eng.set_conv_mode('f16x3')
+    a = eng.fold_host(pf10963, None, 1, 5)
+    b = eng.fold_host(pf10963, None, 1, 5)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    c = eng.fold_host(pf10963, None, -3, -1)                       # predict.py:121-122
+    d = eng.fold_host(pf10963, None, 0, 0)
+    assert np.array_equal(c[0], d[0])
+
+
+@needs_weights
+def test_python_api_and_cli(pf10963, tmp_path):
+    from dmpfold2_b200 import aln_to_coords
+    aln = os.path.join(GOLDEN, 'PF10963.aln')
+    g = np.load(os.path.join(GOLDEN, 'pf10963_n0_m0.npz'))
+    coords, confs, alnmat = aln_to_coords(aln, device='cuda:0', iterations=0, minsteps=0, return_alnmat=True)
+    assert coords.is_cuda and coords.shape == (82, 5, 3) and confs.shape == (82,) and alnmat.dtype == np.uint8
+    _check(coords.cpu().numpy(), confs.cpu().numpy(), g)
+    coords, confs = aln_to_coords(aln, iterations=0, minsteps=0)   # default device string 'cpu' -> CPU tensors
+    assert not coords.is_cuda
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bin', 'dmpfold'), '-i', aln, '-n', '0', '-m', '0'],
+                         capture_output=True, text=True, check=True).stdout.splitlines()
+    assert out[0].startswith('REMARK  CONF:  0.71') and out[-1] == 'END'
+    n_gly = int((pf10963[0] == 7).sum())
+    assert len(out) == 2 + 82 * 5 - n_gly
+    with pytest.raises(RuntimeError):
+        aln_to_coords(aln, template=os.path.join(GOLDEN, 'PF10963.aln'))   # no CA atoms -> size mismatch

@@ -1,0 +1,199 @@
+"""GPU parity tests, stage by stage: every C-ABI stage entry point against the CPU oracle on seeded inputs
+(teacher-forced: each stage gets the oracle's inputs, so errors do not compound)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import GOLDEN, needs_weights
+from oracle import dmpfold_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def eng(state_dict):
+    from dmpfold2_b200.engine import Engine
+    e = Engine(state_dict, 0)
+    yield e
+    e.close()
+
+
+def _rand_msa(n, l, seed):
+    return O.synth_msa_random(l, n, seed)
+
+
+def _nhwc(x_nchw):
+    return x_nchw[0].permute(1, 2, 0).contiguous()
+
+
+def _nchw(x_nhwc):
+    return x_nhwc.permute(2, 0, 1).unsqueeze(0).contiguous()
+
+
+def _rel(a, b):
+    a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize('n,l,seed', [(37, 45, 1), (252, 82, None), (130, 31, 2), (1, 16, 3)])
+def test_reweight_bit_exact(eng, pf10963, n, l, seed):
+    msa = pf10963 if seed is None else _rand_msa(n, l, seed)
+    ref = O.reweight(O.one_hot_msa(torch.from_numpy(msa)))
+    got = eng.reweight(msa).cpu()
+    assert torch.equal(got, ref)
+
+
+def test_dca_features(eng, pf10963):
+    ref = O.msa_features(torch.from_numpy(pf10963))
+    got = eng.dca(pf10963).cpu()
+    assert got.shape == ref.shape == (82, 82, 442)
+    assert (got - ref).abs().max() < 3e-4 * max(1.0, float(ref.abs().max()))
+    # ragged sizes (N, 21L not multiples of the tile sizes) and the single-sequence branch (predict.py:139)
+    msa = _rand_msa(53, 23, 11)
+    ref = O.msa_features(torch.from_numpy(msa))
+    got = eng.dca(msa).cpu()
+    assert (got - ref).abs().max() < 3e-4 * max(1.0, float(ref.abs().max()))
+    assert float(eng.dca(msa[:1]).abs().max()) == 0.0
+
+
+def test_vgru(eng, oracle, pf10963):
+    for msa in (pf10963[:60, :41], _rand_msa(9, 70, 4)):
+        ref = oracle.vgru_last(torch.from_numpy(msa))
+        got = eng.vgru(msa).cpu()
+        assert (got - ref).abs().max() < 5e-5
+
+
+def test_hgru(eng, oracle):
+    g = torch.Generator().manual_seed(7)
+    for l in (19, 82):
+        v = torch.tanh(torch.randn(l, 512, generator=g))
+        ref = oracle.hgru_out(v)
+        got = eng.hgru(v).cpu()
+        assert (got - ref).abs().max() < 5e-5
+
+
+def _conv_ref(oracle, block, x_nchw):
+    sd = oracle.sd
+    y = F.conv2d(x_nchw, sd[f'resnet.{block}.layer1.lin.weight'], sd[f'resnet.{block}.layer1.lin.bias'], padding=2)
+    return y.view(1, 128, 4, y.shape[2], y.shape[3]).max(dim=2)[0]
+
+
+@pytest.mark.parametrize('mode,tol', [('ffma', 2e-5), ('f16x3', 2e-5), ('f16', 3e-3)])
+@pytest.mark.parametrize('l', [16, 27, 82])
+def test_conv5_maxout(eng, oracle, mode, tol, l):
+    g = torch.Generator().manual_seed(100 + l)
+    x = torch.randn(1, 128, l, l, generator=g) * 3
+    eng.set_conv_mode(mode)
+    try:
+        for block in (1, 16):
+            ref = _nhwc(_conv_ref(oracle, block, x))
+            got = eng.conv5_maxout(block, _nhwc(x)).cpu()
+            assert _rel(got, ref) < tol, (mode, l, block, _rel(got, ref))
+    finally:
+        eng.set_conv_mode('ffma')
+
+
+@pytest.mark.parametrize('mode,tol', [('ffma', 5e-5), ('f16x3', 5e-5)])
+def test_resblock(eng, oracle, mode, tol):
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(1, 128, 33, 33, generator=g) * 2
+    eng.set_conv_mode(mode)
+    try:
+        for block in (1, 9):
+            ref = _nhwc(O.resnet_block(x, oracle.sd, block))
+            got = eng.resblock(block, _nhwc(x)).cpu()
+            assert _rel(got, ref) < tol, (mode, block, _rel(got, ref))
+    finally:
+        eng.set_conv_mode('ffma')
+
+
+def test_cse_gate_is_the_weights_only_constant(oracle):
+    # fact 8 of SURVEY.md: avgpool(InstanceNorm_affine(x)) == beta, so the cSE gate does not depend on x
+    g = torch.Generator().manual_seed(2)
+    y = torch.randn(1, 128, 20, 20, generator=g)
+    sd = oracle.sd
+    yn = F.instance_norm(y, weight=sd['resnet.3.layer1.norm.weight'], bias=sd['resnet.3.layer1.norm.bias'])
+    assert (yn.mean(dim=(2, 3))[0] - sd['resnet.3.layer1.norm.bias']).abs().max() < 1e-5
+
+
+@needs_weights
+@pytest.mark.parametrize('mode,tol', [('ffma', 1e-3), ('f16x3', 1e-3)])
+def test_resnet_pass_teacher_forced(eng, oracle, pf10963, mode, tol):
+    taps = {}
+    oracle.fold(pf10963, iterations=0, minsteps=0, taps=taps)
+    x2 = taps['x2'][0]                                   # (443, L, L)
+    feat = x2[:442].permute(1, 2, 0).contiguous()
+    eng.set_conv_mode(mode)
+    try:
+        got = eng.resnet_pass(taps['mat1d'].t().contiguous(), feat, x2[442]).cpu()
+    finally:
+        eng.set_conv_mode('ffma')
+    ref = taps['head'][0]
+    assert _rel(got, ref) < tol, _rel(got, ref)
+
+
+@needs_weights
+def test_head_mds_on_golden_head(eng):
+    g = np.load(os.path.join(GOLDEN, 'pf10963_n0_m0.npz'))
+    head = torch.from_numpy(g['head'])
+    conf_r, m_r, mds_r = O.head_to_mds(head.unsqueeze(0))
+    conf, m, mds = eng.head_mds(head)
+    assert (conf.cpu() - conf_r[0]).abs().max() < 1e-5
+    assert torch.equal(m.cpu(), m_r[0])                  # same fp32 operation order -> bit exact
+    assert (mds.cpu() - mds_r[0]).abs().max() < 3e-3     # oracle eigenvectors are fp32 LAPACK
+    assert (mds.cpu() - torch.from_numpy(g['mds'])).abs().max() < 3e-3
+
+
+@pytest.mark.parametrize('l', [8, 33, 150])
+def test_eig_top8_against_fp64_eigh(eng, l):
+    g = torch.Generator().manual_seed(l)
+    q, _ = torch.linalg.qr(torch.randn(l, l, generator=g, dtype=torch.float64))
+    lam = torch.cat((torch.tensor([-5000.0]), torch.linspace(-50, 40, l - 5, dtype=torch.float64),
+                     torch.tensor([100.0, 100.5, 250.0, 900.0])))[:l]
+    m = (q * lam) @ q.t()
+    m = ((m + m.t()) / 2).float()
+    w, v = torch.linalg.eigh(m.double())
+    v = O.canonical_sign(v)
+    vals, vecs = eng.eig_top8(m)
+    assert (vals.cpu().double() - w[-8:]).abs().max() < 1e-3
+    assert (vecs.cpu().double() - v[:, -8:]).abs().max() < 2e-4
+
+
+def test_coord_gru(eng, oracle):
+    g = torch.Generator().manual_seed(9)
+    l = 41
+    m1 = torch.tanh(torch.randn(512, l, generator=g))
+    mds = torch.randn(l, 8, generator=g) * 5
+    ref = oracle.coord_head(m1, mds)
+    got = eng.coord_gru(m1.t().contiguous(), mds).cpu()
+    assert (got - ref).abs().max() < 2e-4
+
+
+@pytest.mark.parametrize('l,steps', [(12, 1), (82, 100), (300, 20), (1100, 3)])
+def test_refine(eng, l, steps):
+    g = torch.Generator().manual_seed(l)
+    ca = torch.cumsum(torch.randn(l, 3, generator=g) * 1.6, dim=0)
+    ref = O.refine_coords(ca, steps)
+    got = eng.refine(ca, steps).cpu()
+    assert (got - ref).abs().max() < 5e-4
+
+
+@pytest.mark.parametrize('l', [8, 82, 513])
+def test_backbone(eng, l):
+    g = torch.Generator().manual_seed(l)
+    ca = torch.cumsum(torch.randn(l, 3, generator=g) * 2.2, dim=0)
+    ref = O.calpha_to_main_chain(ca.unsqueeze(0))[0].view(l, 5, 3)
+    got = eng.backbone(ca).cpu()
+    assert (got - ref).abs().max() < 1e-4
+    assert torch.equal(got[:, 1], ca)
+
+
+def test_bad_arguments_return_errors(eng):
+    from dmpfold2_b200.engine import Dmp2Error
+    with pytest.raises(Dmp2Error):
+        eng.fold(torch.zeros(4, 5, dtype=torch.uint8))           # L < 8
+    with pytest.raises(Dmp2Error):
+        eng.conv5_maxout(17, torch.zeros(8, 8, 128))

@@ -1,0 +1,103 @@
+"""CPU tests of the host logic and of the C-ABI library surface (no compute without a GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, ROOT
+from oracle import dmpfold_oracle as O
+
+
+def _build():
+    from dmpfold2_b200 import build
+    return build.build()
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    lib_path = _build()
+    lib = ctypes.CDLL(lib_path)
+    header = open(os.path.join(ROOT, 'include', 'dmp2.h')).read()
+    declared = set(re.findall(r'\b(dmp2_[a-z0-9_]+)\s*\(', header))
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), f'{name} declared in include/dmp2.h but not exported'
+    from dmpfold2_b200 import engine
+    assert declared == set(engine.EXPORTS)            # the ctypes binding types every export
+
+
+def test_create_without_gpu_fails_loudly():
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    from dmpfold2_b200.engine import Engine, Dmp2Error
+    with pytest.raises(Dmp2Error):
+        Engine({'embed.weight': torch.eye(22)}, 0)
+    # and through the C ABI directly: an error code, never a crash, never a CPU fallback
+    lib = ctypes.CDLL(_build())
+    lib.dmp2_create.restype = ctypes.c_int
+    lib.dmp2_last_error.restype = ctypes.c_char_p
+    h = ctypes.c_void_p()
+    names = (ctypes.c_char_p * 1)(b'embed.weight')
+    arr = np.eye(22, dtype=np.float32)
+    ptrs = (ctypes.c_void_p * 1)(arr.ctypes.data)
+    numels = (ctypes.c_int64 * 1)(arr.size)
+    st = lib.dmp2_create(ctypes.byref(h), 0, 1, names, ptrs, numels)
+    assert st < 0 and h.value is None
+    assert b'CPU fallback' in lib.dmp2_last_error(None) or b'device' in lib.dmp2_last_error(None)
+
+
+def test_aln_parser_and_encoder_match_reference_semantics(tmp_path):
+    from dmpfold2_b200 import predict as P
+    p = tmp_path / 'x.aln'
+    p.write_text('>hdr\nARNDCQEGHI\n>h2\nLKMFPSTWYV  \nBJOUXZ-.AA\n')
+    rows = P.read_aln(str(p))
+    assert rows == ['ARNDCQEGHI', 'LKMFPSTWYV', 'BJOUXZ-.AA']
+    m = P.encode_aln(rows)
+    assert m.dtype == np.uint8 and m.shape == (3, 10)
+    assert list(m[0]) == list(range(10)) and list(m[1]) == list(range(10, 20))
+    assert list(m[2]) == [20] * 6 + [21, 21, 0, 0]
+    assert np.array_equal(m, O.encode_aln(rows))
+    big = ['ACDEFGHIKL'] * 3005
+    assert P.encode_aln(big).shape == (3000, 10)       # predict.py:130-132
+    real = P.encode_aln(P.read_aln(os.path.join(GOLDEN, 'PF10963.aln')))
+    assert np.array_equal(real, np.load(os.path.join(GOLDEN, 'pf10963_n0_m0.npz'))['alnmat'])
+
+
+def test_template_reader(tmp_path):
+    from dmpfold2_b200 import predict as P
+    g = np.load(os.path.join(GOLDEN, 'pf10963_tmpl_n1_m10.npz'))
+    p = tmp_path / 't.pdb'
+    p.write_text(str(g['pdb_text']) + 'ATOM      1  CB  ALA A   1       1.000   2.000   3.000  1.00  0.00\nHETATM junk\n')
+    ca = P.read_template(str(p))
+    assert ca.shape == (82, 3) and ca.dtype == np.float32
+    assert np.array_equal(ca, O.read_template_ca(str(p)))
+
+
+def test_pdb_writer_format():
+    from dmpfold2_b200 import predict as P
+    coords = torch.arange(2 * 5 * 3, dtype=torch.float32).view(2, 5, 3) * 1.25 - 7
+    confs = torch.tensor([0.5, 0.75])
+    alnmat = np.array([[7, 0]], dtype=np.uint8)          # GLY (no CB), ALA
+    txt = P.format_pdb(coords, confs, alnmat).splitlines()
+    assert txt[0] == 'REMARK  CONF:  0.625'
+    assert txt[-1] == 'END'
+    assert len(txt) == 1 + 4 + 5 + 1
+    assert txt[1] == 'ATOM      1  N   GLY     1      -7.000  -5.750  -4.500  1.00  0.50'
+    assert txt[5] == 'ATOM      5  N   ALA     2      11.750  13.000  14.250  1.00  0.75'
+    assert txt[9].startswith('ATOM      9  CB  ALA     2')
+
+
+def test_cli_flags_match_reference():
+    from dmpfold2_b200 import predict as P
+    with pytest.raises(SystemExit) as ex:
+        P.run_dmpfold(['-h'])
+    assert ex.value.code == 0
+    with pytest.raises(SystemExit):
+        P.run_dmpfold([])                                  # -i is required
+    import inspect
+    sig = inspect.signature(P.aln_to_coords)
+    assert list(sig.parameters) == ['input_file', 'device', 'template', 'iterations', 'minsteps', 'weights_file', 'return_alnmat']
+    assert sig.parameters['device'].default == 'cpu' and sig.parameters['iterations'].default == 10
+    assert sig.parameters['minsteps'].default == 100
