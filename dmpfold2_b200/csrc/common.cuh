@@ -158,6 +158,9 @@ struct dmp2_engine {
     bool ev_ok = false;
     float stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     void* tc_state = nullptr;        // tensor-core conv state (tensor maps), owned by conv_tc.cu
+    bool profile = false;            // record a CUDA-event pair around every conv launch (bench.py roofline)
+    std::vector<cudaEvent_t> prof_ev;
+    size_t prof_used = 0;
 
     int fail(int code, const std::string& msg) {
         status = code;

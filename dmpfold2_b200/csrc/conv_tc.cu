@@ -1,9 +1,399 @@
-// placeholder -- replaced by the tcgen05 kernels
+// Tensor-core 5x5 convolution of the ResNet blocks (network.py:26 inside ResNet_Block, + maxout :30-31) as an
+// implicit GEMM on the 5th-generation tensor cores:  M = L*L pixels, N = 512 output channels, K = 25 taps x 128.
+//
+//   TMA (cp.async.bulk.tensor, 128B swizzle, out-of-bounds zero fill = the pad-2 border)
+//     -> shared-memory rings (A: shifted 8x16-pixel patch x 64 channels; B: 256 couts x 64 channels)
+//     -> tcgen05.mma kind::f16, M=128 N=256 K=16, fp32 accumulators in TMEM (128 lanes x 512 columns = all of it)
+//     -> epilogue warps: tcgen05.ld -> + bias -> max over 4 consecutive couts -> NHWC fp32 store.
+//
+// Precision modes: F16X3 feeds hi+lo fp16 splits of both operands and issues hi*hi + lo*hi + hi*lo
+// (~22-bit effective mantissas, fp32-equivalent for the 1e-3 A parity bar); F16 issues hi*hi only.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue
+// (a warp may only touch TMEM lanes 32*(warp%4)..+31).
 #include "common.cuh"
-int run_conv_tc(dmp2_engine* e, int, const __half*, const __half*, int, float*, int, cudaStream_t) {
-    return e->fail(DMP2_ERR_UNSUPPORTED, "tensor-core conv not built yet");
+#include <cuda.h>
+
+namespace {
+
+constexpr int TILE_M = 128;               // pixels per CTA (8 rows x 16 columns)
+constexpr int TILE_H = 8, TILE_W = 16;
+constexpr int KCHUNK = 64;                // channels per k-block = one 128-byte swizzle row of fp16
+constexpr int A_BYTES = TILE_M * KCHUNK * 2;          // 16 KB
+constexpr int B_BYTES = 256 * KCHUNK * 2;             // 32 KB: 256 couts x 64 cin
+constexpr int NUM_B_SLOTS = 5;
+constexpr int NUM_THREADS = 192;
+
+template <bool SPLIT>
+struct Cfg {
+    static constexpr int A_STAGE_BYTES = SPLIT ? 2 * A_BYTES : A_BYTES;
+    static constexpr int NUM_A_STAGES = SPLIT ? 2 : 4;
+    static constexpr int PIECES = SPLIT ? 4 : 2;      // B pieces per k-block: (hi,n0) (hi,n1) [(lo,n0) (lo,n1)]
+    static constexpr int SMEM_BYTES = NUM_A_STAGES * A_STAGE_BYTES + NUM_B_SLOTS * B_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct TcParams {
+    int gemm;            // 0 = conv (3-D activation map, taps), 1 = plain GEMM test (rows x K)
+    int L;               // conv: image side
+    int tiles_x;         // conv: tiles per image row
+    int num_kb;          // k-blocks: conv 50 (25 taps x 2 chunks), gemm K/64
+    int M;               // gemm: rows
+    float* out;          // conv: raw [L*L][128]; gemm: C [M][512]
+    const float* bias;   // conv: [512]
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-int run_gemm_tn_test(dmp2_engine* e, const float*, const float*, int, int, int, int, float*, cudaStream_t) {
-    return e->fail(DMP2_ERR_UNSUPPORTED, "tensor-core gemm not built yet");
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-void conv_tc_destroy(dmp2_engine*) {}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must never hang the GPU box -- trap after ~2 s instead.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            printf("conv_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr & 0x3FFFF) >> 4);            // start address, bits [0,14)
+    d |= (uint64_t)1 << 16;                            // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset: 8 rows x 128 B
+    d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+    return d;
+}
+// kind::f16 instruction descriptor: fp16 x fp16 -> fp32, both operands K-major, M=128, N=256
+__device__ __forceinline__ uint32_t make_idesc(int m, int n) {
+    return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---- the kernel --------------------------------------------------------------------------------------
+template <bool SPLIT>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+k_conv5_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+           const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const TcParams p) {
+    using C = Cfg<SPLIT>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // 128B swizzle needs 1024-byte alignment
+    const uint32_t a_base = base;
+    const uint32_t b_base = base + C::NUM_A_STAGES * C::A_STAGE_BYTES;
+    const uint32_t bar_base = b_base + NUM_B_SLOTS * B_BYTES;
+    auto a_full = [&](int s) { return bar_base + 8u * s; };
+    auto a_empty = [&](int s) { return bar_base + 8u * (C::NUM_A_STAGES + s); };
+    auto b_full = [&](int s) { return bar_base + 8u * (2 * C::NUM_A_STAGES + s); };
+    auto b_empty = [&](int s) { return bar_base + 8u * (2 * C::NUM_A_STAGES + NUM_B_SLOTS + s); };
+    const uint32_t acc_full = bar_base + 8u * (2 * C::NUM_A_STAGES + 2 * NUM_B_SLOTS);
+    const uint32_t tmem_slot = acc_full + 8;
+    uint8_t* smem_gen = smem_raw + (base - smem_u32(smem_raw));
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - base));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // tile coordinates
+    int x0 = 0, y0 = 0, m0 = 0;
+    if (p.gemm) m0 = blockIdx.x * TILE_M;
+    else { y0 = (blockIdx.x / p.tiles_x) * TILE_H; x0 = (blockIdx.x % p.tiles_x) * TILE_W; }
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < C::NUM_A_STAGES; s++) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
+        for (int s = 0; s < NUM_B_SLOTS; s++) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+        mbar_init(acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_gen;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int sa = 0, pa = 0, sb = 0, pb = 0;
+            for (int kb = 0; kb < p.num_kb; kb++) {
+                int c0, c1, c2;
+                if (p.gemm) { c0 = kb * KCHUNK; c1 = m0; c2 = 0; }
+                else {
+                    int tap = kb >> 1, kc = kb & 1;
+                    int dy = tap / 5, dx = tap - dy * 5;
+                    c0 = kc * KCHUNK; c1 = x0 + dx - 2; c2 = y0 + dy - 2;
+                }
+                mbar_wait(a_empty(sa), pa ^ 1);
+                mbar_expect_tx(a_full(sa), C::A_STAGE_BYTES);
+                tma_load_3d(a_base + sa * C::A_STAGE_BYTES, &map_a_hi, a_full(sa), c0, c1, c2);
+                if (SPLIT) tma_load_3d(a_base + sa * C::A_STAGE_BYTES + A_BYTES, &map_a_lo, a_full(sa), c0, c1, c2);
+                if (++sa == C::NUM_A_STAGES) { sa = 0; pa ^= 1; }
+                const int k0 = kb * KCHUNK;               // weights are [512][K] with k = tap*128 + c = kb*64 + ...
+                for (int piece = 0; piece < C::PIECES; piece++) {
+                    mbar_wait(b_empty(sb), pb ^ 1);
+                    mbar_expect_tx(b_full(sb), B_BYTES);
+                    tma_load_2d(b_base + sb * B_BYTES, piece < 2 ? &map_b_hi : &map_b_lo, b_full(sb), k0, (piece & 1) * 256);
+                    if (++sb == NUM_B_SLOTS) { sb = 0; pb ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(128, 256);
+            int sa = 0, pa = 0, sb = 0, pb = 0;
+            for (int kb = 0; kb < p.num_kb; kb++) {
+                mbar_wait(a_full(sa), pa);
+                const uint32_t a_hi = a_base + sa * C::A_STAGE_BYTES;
+                const uint32_t a_lo = a_hi + A_BYTES;
+                for (int piece = 0; piece < C::PIECES; piece++) {
+                    mbar_wait(b_full(sb), pb);
+                    tc_fence_after();
+                    const uint32_t b_addr = b_base + sb * B_BYTES;
+                    const uint32_t d = tmem_base + (uint32_t)(piece & 1) * 256u;
+                    const bool first = (kb == 0) && (piece < 2);          // first touch of this accumulator half
+#pragma unroll
+                    for (int k = 0; k < KCHUNK / 16; k++)
+                        tc_mma_f16(d, make_smem_desc(a_hi + k * 32), make_smem_desc(b_addr + k * 32), idesc, !(first && k == 0));
+                    if (SPLIT && piece < 2) {                              // lo(A) x hi(B)
+#pragma unroll
+                        for (int k = 0; k < KCHUNK / 16; k++)
+                            tc_mma_f16(d, make_smem_desc(a_lo + k * 32), make_smem_desc(b_addr + k * 32), idesc, 1u);
+                    }
+                    tc_commit(b_empty(sb));
+                    if (++sb == NUM_B_SLOTS) { sb = 0; pb ^= 1; }
+                }
+                tc_commit(a_empty(sa));
+                if (++sa == C::NUM_A_STAGES) { sa = 0; pa ^= 1; }
+            }
+            tc_commit(acc_full);
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int q = warp & 3;                      // TMEM lane quarter this warp may access
+        const int r = q * 32 + lane;                 // accumulator row = pixel within the tile
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        bool valid;
+        int64_t row;
+        if (p.gemm) { valid = (m0 + r) < p.M; row = m0 + r; }
+        else {
+            int y = y0 + (r >> 4), x = x0 + (r & 15);
+            valid = (y < p.L) && (x < p.L);
+            row = (int64_t)y * p.L + x;
+        }
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        for (int ch = 0; ch < 16; ch++) {
+            uint32_t v[32];
+            tmem_ld32(lane_addr + ch * 32, v);
+            if (!valid) continue;
+            if (p.gemm) {
+                float4* dst = reinterpret_cast<float4*>(p.out + row * 512 + ch * 32);
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+                    dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                                         __uint_as_float(v[4 * i + 3]));
+            } else {
+                float o[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + ch * 32 + 4 * i));
+                    o[i] = fmaxf(fmaxf(__uint_as_float(v[4 * i]) + b.x, __uint_as_float(v[4 * i + 1]) + b.y),
+                                 fmaxf(__uint_as_float(v[4 * i + 2]) + b.z, __uint_as_float(v[4 * i + 3]) + b.w));
+                }
+                float4* dst = reinterpret_cast<float4*>(p.out + row * 128 + ch * 8);
+                dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+                dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+// ---- host side: tensor maps -----------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct TcState {
+    EncodeTiledFn encode = nullptr;
+    CUtensorMap wmap[DMP2_NBLOCKS][2];
+    bool wmap_ok[DMP2_NBLOCKS] = {false};
+    CUtensorMap amap[2];
+    const void* amap_ptr[2] = {nullptr, nullptr};
+    int amap_L = 0;
+    bool attr_set = false;
+    std::vector<void*> test_allocs;
+};
+
+int get_state(dmp2_engine* e, TcState** out) {
+    if (!e->tc_state) {
+        TcState* s = new TcState();
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t c = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (c != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+            delete s;
+            return e->fail(DMP2_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+        }
+        s->encode = (EncodeTiledFn)fn;
+        e->tc_state = s;
+    }
+    TcState* s = (TcState*)e->tc_state;
+    if (!s->attr_set) {
+        CUDA_TRY(e, cudaFuncSetAttribute(k_conv5_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<true>::SMEM_BYTES));
+        CUDA_TRY(e, cudaFuncSetAttribute(k_conv5_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<false>::SMEM_BYTES));
+        s->attr_set = true;
+    }
+    *out = s;
+    return 0;
+}
+
+// fp16 tensor [d2][d1][d0] (d0 contiguous), box [b2][b1][64], 128B swizzle, zero OOB fill
+int encode_map(dmp2_engine* e, TcState* s, CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims,
+               const uint64_t* strides_bytes, const uint32_t* box) {
+    cuuint64_t gdim[3], gstr[2];
+    cuuint32_t bx[3], estr[3] = {1, 1, 1};
+    for (int i = 0; i < rank; i++) { gdim[i] = dims[i]; bx[i] = box[i]; }
+    for (int i = 0; i < rank - 1; i++) gstr[i] = strides_bytes[i];
+    CUresult r = s->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gdim, gstr, bx, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return e->fail(DMP2_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+    return 0;
+}
+
+int weight_map(dmp2_engine* e, TcState* s, CUtensorMap* map, const __half* w, int K) {
+    uint64_t dims[2] = {(uint64_t)K, 512};
+    uint64_t str[1] = {(uint64_t)K * 2};
+    uint32_t box[2] = {KCHUNK, 256};
+    return encode_map(e, s, map, w, 2, dims, str, box);
+}
+
+template <bool SPLIT>
+int launch(dmp2_engine* e, const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
+           const TcParams& p, int grid, cudaStream_t st) {
+    k_conv5_tc<SPLIT><<<grid, NUM_THREADS, Cfg<SPLIT>::SMEM_BYTES, st>>>(ah, al, bh, bl, p);
+    POST_LAUNCH(e, "k_conv5_tc");
+    return 0;
+}
+
+}  // namespace
+
+int run_conv_tc(dmp2_engine* e, int blk, const __half* xh, const __half* xl, int L, float* raw, int mode, cudaStream_t st) {
+    TcState* s;
+    TRY(get_state(e, &s));
+    if (!s->wmap_ok[blk]) {
+        TRY(weight_map(e, s, &s->wmap[blk][0], e->w.blk[blk].w_hi, 3200));
+        TRY(weight_map(e, s, &s->wmap[blk][1], e->w.blk[blk].w_lo, 3200));
+        s->wmap_ok[blk] = true;
+    }
+    if (s->amap_ptr[0] != xh || s->amap_ptr[1] != xl || s->amap_L != L) {
+        uint64_t dims[3] = {128, (uint64_t)L, (uint64_t)L};
+        uint64_t str[2] = {256, (uint64_t)L * 256};
+        uint32_t box[3] = {KCHUNK, TILE_W, TILE_H};
+        TRY(encode_map(e, s, &s->amap[0], xh, 3, dims, str, box));
+        TRY(encode_map(e, s, &s->amap[1], xl, 3, dims, str, box));
+        s->amap_ptr[0] = xh; s->amap_ptr[1] = xl; s->amap_L = L;
+    }
+    TcParams p;
+    p.gemm = 0; p.L = L; p.tiles_x = cdiv(L, TILE_W); p.num_kb = 50; p.M = L * L; p.out = raw; p.bias = e->w.blk[blk].bias;
+    int grid = p.tiles_x * cdiv(L, TILE_H);
+    if (mode == DMP2_CONV_TC_F16X3) return launch<true>(e, s->amap[0], s->amap[1], s->wmap[blk][0], s->wmap[blk][1], p, grid, st);
+    return launch<false>(e, s->amap[0], s->amap[1], s->wmap[blk][0], s->wmap[blk][1], p, grid, st);
+}
+
+// C[M,512] = A[M,K] * B[512,K]^T through the same TMA / tcgen05 / TMEM pipeline (descriptor + pipeline self-test)
+int run_gemm_tn_test(dmp2_engine* e, const float* a, const float* b, int M, int N, int K, int mode, float* c, cudaStream_t st) {
+    if (N != 512 || K % KCHUNK != 0 || M < 1) return e->fail(DMP2_ERR_BAD_ARG, "gemm_tn_test: need N == 512 and K % 64 == 0");
+    if (mode != DMP2_CONV_TC_F16X3 && mode != DMP2_CONV_TC_F16) return e->fail(DMP2_ERR_BAD_ARG, "gemm_tn_test: tensor-core modes only");
+    TcState* s;
+    TRY(get_state(e, &s));
+    __half *ah, *al, *bh, *bl;
+    const int64_t na = (int64_t)M * K, nb = (int64_t)N * K;
+    CUDA_TRY(e, cudaMalloc(&ah, na * 2)); CUDA_TRY(e, cudaMalloc(&al, na * 2));
+    CUDA_TRY(e, cudaMalloc(&bh, nb * 2)); CUDA_TRY(e, cudaMalloc(&bl, nb * 2));
+    int rc = 0;
+    do {
+        if ((rc = run_split_half(e, a, na, ah, al, st))) break;
+        if ((rc = run_split_half(e, b, nb, bh, bl, st))) break;
+        CUtensorMap mah, mal, mbh, mbl;
+        uint64_t dims[3] = {(uint64_t)K, (uint64_t)M, 1};
+        uint64_t str[2] = {(uint64_t)K * 2, (uint64_t)K * 2 * (uint64_t)M};
+        uint32_t box[3] = {KCHUNK, TILE_M, 1};
+        if ((rc = encode_map(e, s, &mah, ah, 3, dims, str, box))) break;
+        if ((rc = encode_map(e, s, &mal, al, 3, dims, str, box))) break;
+        if ((rc = weight_map(e, s, &mbh, bh, K))) break;
+        if ((rc = weight_map(e, s, &mbl, bl, K))) break;
+        TcParams p;
+        p.gemm = 1; p.L = 0; p.tiles_x = 1; p.num_kb = K / KCHUNK; p.M = M; p.out = c; p.bias = nullptr;
+        int grid = cdiv(M, TILE_M);
+        rc = (mode == DMP2_CONV_TC_F16X3) ? launch<true>(e, mah, mal, mbh, mbl, p, grid, st)
+                                          : launch<false>(e, mah, mal, mbh, mbl, p, grid, st);
+    } while (0);
+    cudaStreamSynchronize(st);
+    cudaFree(ah); cudaFree(al); cudaFree(bh); cudaFree(bl);
+    return rc;
+}
+
+void conv_tc_destroy(dmp2_engine* e) {
+    if (e->tc_state) {
+        delete (TcState*)e->tc_state;
+        e->tc_state = nullptr;
+    }
+}

@@ -356,6 +356,7 @@ void dmp2_destroy(dmp2_engine* e) {
     free_workspace(e);
     for (void* p : e->weight_allocs) cudaFree(p);
     if (e->ev_ok) for (int i = 0; i < 16; i++) cudaEventDestroy(e->ev[i]);
+    for (auto& ev : e->prof_ev) cudaEventDestroy(ev);
     delete e;
 }
 
@@ -373,6 +374,34 @@ int dmp2_stage_times(const dmp2_engine* e, float* out_ms, int cap) {
     int n = std::min(cap, 6);
     for (int i = 0; i < n; i++) out_ms[i] = e->stage_ms[i];
     return n;
+}
+
+int dmp2_set_profile(dmp2_engine* e, int on) {
+    if (!e) return DMP2_ERR_BAD_ARG;
+    TRY(check_device(e));
+    if (on && e->prof_ev.empty()) {
+        e->prof_ev.resize(2 * DMP2_NBLOCKS * 128);
+        for (auto& ev : e->prof_ev) CUDA_TRY(e, cudaEventCreate(&ev));
+    }
+    e->profile = on != 0;
+    e->prof_used = 0;
+    return 0;
+}
+
+int dmp2_conv_profile(dmp2_engine* e, int* n_launches, float* total_ms) {
+    if (!e || !n_launches || !total_ms) return DMP2_ERR_BAD_ARG;
+    TRY(check_device(e));
+    CUDA_TRY(e, cudaDeviceSynchronize());
+    float tot = 0.f;
+    for (size_t i = 0; i + 1 < e->prof_used; i += 2) {
+        float ms = 0.f;
+        CUDA_TRY(e, cudaEventElapsedTime(&ms, e->prof_ev[i], e->prof_ev[i + 1]));
+        tot += ms;
+    }
+    *n_launches = (int)(e->prof_used / 2);
+    *total_ms = tot;
+    e->prof_used = 0;
+    return 0;
 }
 
 int dmp2_fold(dmp2_engine* e, const uint8_t* msa_dev, int N, int L, const float* tmpl_ca_dev, int iterations, int minsteps,

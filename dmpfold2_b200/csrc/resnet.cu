@@ -204,8 +204,11 @@ int run_conv_ffma(dmp2_engine* e, int blk, const float* x, int L, float* raw, cu
 // One ResNet block in place on ws.x (and its fp16 split ws.xh/xl).
 int run_resblock(dmp2_engine* e, int blk, int L, cudaStream_t st) {
     Workspace& ws = e->ws;
+    const bool prof = e->profile && e->prof_used + 2 <= e->prof_ev.size();
+    if (prof) cudaEventRecord(e->prof_ev[e->prof_used], st);
     if (e->conv_mode == DMP2_CONV_FFMA) TRY(run_conv_ffma(e, blk, ws.x, L, ws.raw, st));
     else TRY(run_conv_tc(e, blk, ws.xh, ws.xl, L, ws.raw, e->conv_mode, st));
+    if (prof) { cudaEventRecord(e->prof_ev[e->prof_used + 1], st); e->prof_used += 2; }
     return run_norm_gate(e, blk, ws.raw, ws.x, L, false, st);
 }
 

@@ -29,6 +29,8 @@ _SIGS = {
     'dmp2_set_conv_mode': (_i, [_vp, _i]),
     'dmp2_launch_count': (_i64, [_vp]),
     'dmp2_stage_times': (_i, [_vp, C.POINTER(C.c_float), _i]),
+    'dmp2_set_profile': (_i, [_vp, _i]),
+    'dmp2_conv_profile': (_i, [_vp, C.POINTER(_i), C.POINTER(C.c_float)]),
     'dmp2_fold': (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp]),
     'dmp2_fold_host': (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _vp]),
     'dmp2_reweight': (_i, [_vp, _vp, _i, _i, _vp, _vp]),
@@ -131,6 +133,15 @@ class Engine:
         buf = (C.c_float * 8)()
         n = self.lib.dmp2_stage_times(self.h, buf, 8)
         return {STAGE_NAMES[i]: float(buf[i]) for i in range(n)}
+
+    def set_profile(self, on: bool):
+        self._check(self.lib.dmp2_set_profile(self.h, 1 if on else 0), 'dmp2_set_profile')
+
+    def conv_profile(self) -> Tuple[int, float]:
+        """(number of conv launches, their summed device time in ms) since the last call."""
+        n, ms = C.c_int(), C.c_float()
+        self._check(self.lib.dmp2_conv_profile(self.h, C.byref(n), C.byref(ms)), 'dmp2_conv_profile')
+        return n.value, ms.value
 
     # ---- the hot path --------------------------------------------------------------------------
     def fold(self, msa: torch.Tensor, template_ca: Optional[torch.Tensor] = None, iterations: int = 10,

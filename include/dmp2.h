@@ -63,6 +63,12 @@ int64_t dmp2_launch_count(const dmp2_engine* e);
  * features, vgru, hgru, stem, resnet(conv+norm), head+eig, coord_gru, refine+backbone.  Returns n. */
 int dmp2_stage_times(const dmp2_engine* e, float* out_ms, int cap);
 
+/* Roofline support: when on, a CUDA-event pair is recorded (on the launching stream) around every 5x5-conv
+ * kernel launch; dmp2_conv_profile synchronises the device, returns the number of launches seen and their
+ * summed device time since the last call, and resets the counters. */
+int dmp2_set_profile(dmp2_engine* e, int on);
+int dmp2_conv_profile(dmp2_engine* e, int* n_launches, float* total_ms);
+
 /* ---- the hot path: replaces network(inputs, inputs2, nloops, refine_steps) + predict.py:136-147 ---- */
 
 /* msa_dev: uint8 N x L row-major residue codes 0..21 as produced by predict.py:124-128 (row 0 = query).

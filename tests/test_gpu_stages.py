@@ -197,3 +197,15 @@ def test_bad_arguments_return_errors(eng):
         eng.fold(torch.zeros(4, 5, dtype=torch.uint8))           # L < 8
     with pytest.raises(Dmp2Error):
         eng.conv5_maxout(17, torch.zeros(8, 8, 128))
+
+
+@pytest.mark.parametrize('mode,tol', [('f16x3', 5e-5), ('f16', 2e-3)])
+@pytest.mark.parametrize('m,k', [(128, 64), (300, 256), (1000, 3200)])
+def test_tensor_core_gemm_core(eng, mode, tol, m, k):
+    """TMA -> tcgen05 -> TMEM pipeline self-test on a plain GEMM (descriptors, swizzle, barriers, epilogue)."""
+    g = torch.Generator().manual_seed(m + k)
+    a = torch.randn(m, k, generator=g)
+    b = torch.randn(512, k, generator=g) * 0.1
+    ref = a.double() @ b.double().t()
+    got = eng.gemm_tn_test(a, b, mode).cpu().double()
+    assert _rel(got, ref) < tol, _rel(got, ref)
