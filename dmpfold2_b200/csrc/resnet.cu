@@ -49,21 +49,39 @@ __global__ void __launch_bounds__(256) k_stem_update(const float* __restrict__ b
 // InstanceNorm statistics (biased variance over all L*L pixels per channel, eps 1e-5), deterministic:
 // per-CTA fp64 partials, the last CTA to finish folds them in a fixed order.
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_in_stats(const float* __restrict__ raw, int64_t npix, const float* __restrict__ gamma,
-                                                  double* __restrict__ part, unsigned int* __restrict__ ticket,
-                                                  float* __restrict__ norm /* [mean 128 | gamma*rstd 128] */) {
-    const int c = threadIdx.x & 127, par = threadIdx.x >> 7;
-    double s = 0, ss = 0;
-    for (int64_t p = (int64_t)blockIdx.x * 2 + par; p < npix; p += (int64_t)gridDim.x * 2) {
-        double v = (double)raw[p * 128 + c];
-        s += v; ss += v * v;
+__global__ void __launch_bounds__(512) k_in_stats(const float* __restrict__ raw, int64_t npix, const float* __restrict__ gamma,
+                                                   double* __restrict__ part, unsigned int* __restrict__ ticket,
+                                                   float* __restrict__ norm /* [mean 128 | gamma*rstd 128] */) {
+    // 32 lanes x float4 cover one pixel's 128 channels; 16 pixel groups per CTA; 4 loads in flight per thread
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    double s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
+    const int64_t stride = (int64_t)gridDim.x * 16;
+    int64_t p = (int64_t)blockIdx.x * 16 + grp;
+    for (; p + 3 * stride < npix; p += 4 * stride) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) v[u] = *reinterpret_cast<const float4*>(raw + (p + u * stride) * 128 + lane * 4);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            s[0] += v[u].x; s[1] += v[u].y; s[2] += v[u].z; s[3] += v[u].w;
+            ss[0] += (double)v[u].x * v[u].x; ss[1] += (double)v[u].y * v[u].y;
+            ss[2] += (double)v[u].z * v[u].z; ss[3] += (double)v[u].w * v[u].w;
+        }
     }
-    __shared__ double sh[2][256];
-    sh[0][threadIdx.x] = s; sh[1][threadIdx.x] = ss;
+    for (; p < npix; p += stride) {
+        float4 v = *reinterpret_cast<const float4*>(raw + p * 128 + lane * 4);
+        s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+        ss[0] += (double)v.x * v.x; ss[1] += (double)v.y * v.y; ss[2] += (double)v.z * v.z; ss[3] += (double)v.w * v.w;
+    }
+    __shared__ double sh[16][256];                    // [group][sum 128 | sumsq 128]
+#pragma unroll
+    for (int u = 0; u < 4; u++) { sh[grp][lane * 4 + u] = s[u]; sh[grp][128 + lane * 4 + u] = ss[u]; }
     __syncthreads();
-    if (par == 0) {
-        part[(int64_t)blockIdx.x * 256 + c] = sh[0][c] + sh[0][c + 128];
-        part[(int64_t)blockIdx.x * 256 + 128 + c] = sh[1][c] + sh[1][c + 128];
+    if (threadIdx.x < 256) {
+        double t = 0;
+#pragma unroll 8
+        for (int g = 0; g < 16; g++) t += sh[g][threadIdx.x];
+        part[(int64_t)blockIdx.x * 256 + threadIdx.x] = t;
     }
     __threadfence();
     __shared__ bool last;
@@ -72,14 +90,21 @@ __global__ void __launch_bounds__(256) k_in_stats(const float* __restrict__ raw,
     __syncthreads();
     if (!last) return;
     __threadfence();
+    // fixed-order fold of the CTA partials: 2 threads per column, then a fixed combine
+    {
+        const int col = threadIdx.x & 255, q = threadIdx.x >> 8;
+        double t = 0;
+#pragma unroll 8
+        for (unsigned b = q; b < gridDim.x; b += 2) t += part[(int64_t)b * 256 + col];
+        sh[q][col] = t;
+    }
+    __syncthreads();
     if (threadIdx.x < 128) {
-        double ts = 0, tss = 0;
-        for (unsigned b = 0; b < gridDim.x; b++) {
-            ts += part[(int64_t)b * 256 + c];
-            tss += part[(int64_t)b * 256 + 128 + c];
-        }
-        double mean = ts / (double)npix;
-        double var = tss / (double)npix - mean * mean;
+        const int c = threadIdx.x;
+        double sum = sh[0][c] + sh[1][c];
+        double sq = sh[0][128 + c] + sh[1][128 + c];
+        double mean = sum / (double)npix;
+        double var = sq / (double)npix - mean * mean;
         if (var < 0) var = 0;
         norm[c] = (float)mean;
         norm[128 + c] = (float)((double)gamma[c] / sqrt(var + 1e-5));
@@ -159,8 +184,8 @@ int run_norm_gate(dmp2_engine* e, int blk, const float* raw, float* x, int L, bo
     const int64_t npix = (int64_t)L * L;
     const float* gamma = stem ? e->w.stem_gamma : e->w.blk[blk].gamma;
     const float* beta = stem ? e->w.stem_beta : e->w.blk[blk].beta;
-    int sgrid = (int)std::min<int64_t>(cdiv64(npix, 64), (int64_t)e->num_sms * 4);
-    k_in_stats<<<sgrid, 256, 0, st>>>(raw, npix, gamma, ws.stat_part, ws.ticket, ws.norm_ss);
+    int sgrid = (int)std::min<int64_t>(cdiv64(npix, 64), (int64_t)e->num_sms * 2);
+    k_in_stats<<<sgrid, 512, 0, st>>>(raw, npix, gamma, ws.stat_part, ws.ticket, ws.norm_ss);
     POST_LAUNCH(e, "k_in_stats");
     int agrid = (int)std::min<int64_t>(cdiv64(npix, 8), (int64_t)e->num_sms * 8);
     k_norm_gate<<<agrid, 256, 0, st>>>(raw, ws.norm_ss, beta, stem ? nullptr : e->w.blk[blk].gate_c,
