@@ -81,6 +81,12 @@ struct Weights {
     float* vg_b0;            // [2048]         b_hh_l0 in the same order
     float* vg_w1;            // [2048][1024]   4j+0/1: [W_ih_l1 | W_hh_l1] (r,z); 4j+2: [W_ih_n | 0]; 4j+3: [0 | W_hh_n]
     float* vg_b1;            // [2048]         (b_ih_r+b_hh_r, b_ih_z+b_hh_z, b_ih_n, b_hh_n)
+    // vgru, tensor-core path: rows packed [slice of 32 units][gate r|z|n][32] for the three K=512 GEMM roles
+    // (0: W_hh_l0, 1: W_ih_l1, 2: W_hh_l1), fp16 hi/lo split
+    __half* vt_w_hi[3];
+    __half* vt_w_lo[3];
+    float* vt_bias[3];       // [1536] each, same packed order (b_hh_l0, b_ih_l1, b_hh_l1)
+    float* vt_gi0;           // [22][1536] W_ih_l0 column gather + b_ih_l0, packed order
     BiGruLayer hgru[2];
     BiGruLayer cgru[3];
     float* coord_fc;         // [3][512]
@@ -113,6 +119,8 @@ struct Workspace {
     float* feat = nullptr;         // [L*L][444]
     // 1-D track
     float* vg_h = nullptr;         // [2 layers][2 buffers][L][512]
+    __half* vt_h16 = nullptr;      // [4 buffers][hi|lo][L][512] fp16 split of the vgru states
+    float* vt_gi1 = nullptr;       // [2][L][1536] layer-1 input projections in flight
     float* v_last = nullptr;       // [L][512]
     float* gi = nullptr;           // [L][1536] input projections of the current bi-GRU layer
     float* seq_a = nullptr;        // [L][520] layer input / output ping
@@ -158,6 +166,8 @@ struct dmp2_engine {
     bool ev_ok = false;
     float stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     void* tc_state = nullptr;        // tensor-core conv state (tensor maps), owned by conv_tc.cu
+    void* vt_state = nullptr;        // tensor-core vgru state, owned by vgru_tc.cu
+    int vgru_mode = 0;               // 0 = tensor cores (fp16x3), 1 = CUDA-core fp32 validation path
     bool profile = false;            // record a CUDA-event pair around every conv launch (bench.py roofline)
     std::vector<cudaEvent_t> prof_ev;
     size_t prof_used = 0;
@@ -179,6 +189,9 @@ int run_feat_export(dmp2_engine* e, const float* feat444, int L, float* feat442,
 int run_feat_import(dmp2_engine* e, const float* feat442, int L, float* feat444, cudaStream_t st);
 // gru.cu
 int run_vgru(dmp2_engine* e, const uint8_t* msa, int N, int L, float* out, cudaStream_t st);
+int run_vgru_ffma(dmp2_engine* e, const uint8_t* msa, int N, int L, float* out, cudaStream_t st);
+int run_vgru_tc(dmp2_engine* e, const uint8_t* msa, int N, int L, float* out, cudaStream_t st);
+void vgru_tc_destroy(dmp2_engine* e);
 int run_bigru(dmp2_engine* e, const BiGruLayer* layers, int nlayers, const float* in, int L, float* out, cudaStream_t st);
 int run_coord_head(dmp2_engine* e, const float* mat1d_t, const float* mds, int L, float* ca, cudaStream_t st);
 // resnet.cu

@@ -91,6 +91,37 @@ static int load_weights(dmp2_engine* e, HostSD& sd) {
             b1[4 * j + 2] = bih1[1024 + j];
             b1[4 * j + 3] = bhh1[1024 + j];
         }
+        // tensor-core packing: row (slice*96 + g*32 + ul) <- gate g of hidden unit slice*32 + ul
+        const float* mats[3] = {whh0, wih1, whh1};
+        const float* biases[3] = {bhh0, bih1, bhh1};
+        for (int r = 0; r < 3; r++) {
+            std::vector<__half> wh((size_t)1536 * 512), wl((size_t)1536 * 512);
+            std::vector<float> bp(1536);
+            for (int sl = 0; sl < 16; sl++)
+                for (int g = 0; g < 3; g++)
+                    for (int ul = 0; ul < 32; ul++) {
+                        const int pr = sl * 96 + g * 32 + ul, src = g * 512 + sl * 32 + ul;
+                        bp[pr] = biases[r][src];
+                        for (int k = 0; k < 512; k++) {
+                            float v = mats[r][(size_t)src * 512 + k];
+                            __half h = __float2half_rn(v);
+                            wh[(size_t)pr * 512 + k] = h;
+                            wl[(size_t)pr * 512 + k] = __float2half_rn(v - __half2float(h));
+                        }
+                    }
+            TRY(upload(e, wh, &w.vt_w_hi[r])); TRY(upload(e, wl, &w.vt_w_lo[r])); TRY(upload(e, bp, &w.vt_bias[r]));
+        }
+        {
+            std::vector<float> g0((size_t)22 * 1536);
+            for (int code = 0; code < 22; code++)
+                for (int sl = 0; sl < 16; sl++)
+                    for (int g = 0; g < 3; g++)
+                        for (int ul = 0; ul < 32; ul++) {
+                            const int src = g * 512 + sl * 32 + ul;
+                            g0[(size_t)code * 1536 + sl * 96 + g * 32 + ul] = wih0[(size_t)src * 22 + code] + bih0[src];
+                        }
+            TRY(upload(e, g0, &w.vt_gi0));
+        }
         TRY(upload(e, gi0, &w.vg_gi0)); TRY(upload(e, w0, &w.vg_w0)); TRY(upload(e, b0, &w.vg_b0));
         TRY(upload(e, w1, &w.vg_w1)); TRY(upload(e, b1, &w.vg_b1));
     }
@@ -211,6 +242,8 @@ int ensure_workspace(dmp2_engine* e, int L, int N) {
     TRY(wsalloc(e, &ws.apc, 2 * L + 1));
     TRY(wsalloc(e, &ws.feat, P * DMP2_FEAT_LD));
     TRY(wsalloc(e, &ws.vg_h, 4 * (int64_t)L * 512));
+    TRY(wsalloc(e, &ws.vt_h16, 8 * (int64_t)L * 512));
+    TRY(wsalloc(e, &ws.vt_gi1, 2 * (int64_t)L * 1536));
     TRY(wsalloc(e, &ws.v_last, (int64_t)L * 512));
     TRY(wsalloc(e, &ws.gi, (int64_t)L * 1536));
     TRY(wsalloc(e, &ws.seq_a, (int64_t)L * 520));
@@ -344,6 +377,8 @@ int dmp2_create(dmp2_engine** out, int device, int n_tensors, const char* const*
         else if (!strcmp(mode, "f16")) e->conv_mode = DMP2_CONV_TC_F16;
         else if (!strcmp(mode, "ffma")) e->conv_mode = DMP2_CONV_FFMA;
     }
+    const char* vm = getenv("DMP2_VGRU");
+    if (vm && !strcmp(vm, "ffma")) e->vgru_mode = 1;
     *out = e;
     return 0;
 }
@@ -353,6 +388,7 @@ void dmp2_destroy(dmp2_engine* e) {
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
     conv_tc_destroy(e);
+    vgru_tc_destroy(e);
     free_workspace(e);
     for (void* p : e->weight_allocs) cudaFree(p);
     if (e->ev_ok) for (int i = 0; i < 16; i++) cudaEventDestroy(e->ev[i]);

@@ -54,6 +54,10 @@ struct LoadConcat2 {             // A(m,k) = k < k1 ? p1[m*ld1+k] : p2[m*ld2 + k
 };
 
 int run_vgru(dmp2_engine* e, const uint8_t* msa, int N, int L, float* out, cudaStream_t st) {
+    return e->vgru_mode == 0 ? run_vgru_tc(e, msa, N, L, out, st) : run_vgru_ffma(e, msa, N, L, out, st);
+}
+
+int run_vgru_ffma(dmp2_engine* e, const uint8_t* msa, int N, int L, float* out, cudaStream_t st) {
     const Weights& w = e->w;
     const int64_t hsz = (int64_t)L * 512;
     float* h0[2] = {e->ws.vg_h, e->ws.vg_h + hsz};

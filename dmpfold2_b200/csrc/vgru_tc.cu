@@ -1,0 +1,269 @@
+// vgru on the tensor cores (network.py:223-224): 2-layer GRU(22 -> 512 -> 512) scanned down the N rows of the
+// MSA, batch = the L alignment columns; only the state after the last row is kept.
+//
+// The recurrence is split into three K=512 GEMM roles that run as a 3-stage wavefront, ONE launch per step:
+//   role 0  (time t = s)    gh0 = h0[t-1] W_hh0^T  -> layer-0 cell (input term = column gather of W_ih0) -> h0[t]
+//   role 1  (time t = s-1)  gi1 = h0[t]   W_ih1^T + b_ih1                                   -> gi1[t] (fp32, global)
+//   role 2  (time t = s-2)  gh1 = h1[t-1] W_hh1^T  -> layer-1 cell with gi1[t]                       -> h1[t]
+// Each CTA owns a 128-row x 32-hidden-unit tile: M=128, N=96 (gates r|z|n of its 32 units), K=512, computed as
+// TMA -> smem ring -> tcgen05.mma (fp16 hi/lo split of both operands, 3 MMAs, fp32 accumulate in TMEM) ->
+// epilogue warps apply the GRU cell and write h as fp32 + fp16 hi/lo (the next step's A operand).
+// GRU weights do not tolerate single-pass fp16/tf32, hence the 3-term split.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+using namespace tc;
+
+constexpr int VT_N = 96;                       // accumulator columns per CTA: 3 gates x 32 units
+constexpr int VT_NKB = 8;                      // K = 512 in chunks of 64
+constexpr int VT_A_BYTES = 128 * 64 * 2;       // 16 KB
+constexpr int VT_B_BYTES = VT_N * 64 * 2;      // 12 KB
+constexpr int VT_STAGE_BYTES = 2 * VT_A_BYTES + 2 * VT_B_BYTES;     // 56 KB
+constexpr int VT_STAGES = 4;
+constexpr int VT_SMEM = VT_STAGES * VT_STAGE_BYTES + 1024 + 256;
+constexpr int VT_THREADS = 192;
+
+struct VtMaps {
+    CUtensorMap a_hi[4], a_lo[4];              // h buffers: 0,1 = h0 ping/pong, 2,3 = h1 ping/pong
+    CUtensorMap b_hi[3], b_lo[3];              // packed weights of the three roles
+};
+
+struct VtRole {
+    int active;
+    int a_sel;                                 // which h buffer is the A operand
+    const float* bias;                         // [1536] packed
+    const float* gi;                           // role 0: gi0 table [22][1536]; role 2: gi1 [L][1536]; role 1: unused
+    const float* h_old;                        // fp32 previous state [L][512] (roles 0, 2)
+    float* out_f32;                            // roles 0,2: new state [L][512]; role 1: gi1 [L][1536]
+    __half* out_hi;
+    __half* out_lo;
+};
+
+struct VtParams {
+    int L;
+    const uint8_t* codes;                      // MSA row consumed by role 0 this step: [L]
+    VtRole role[3];
+};
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* r) {
+    uint32_t u[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+                 : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; i++) r[i] = __uint_as_float(u[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__global__ void __launch_bounds__(VT_THREADS, 1) k_vgru_step(const __grid_constant__ VtMaps maps, const VtParams p) {
+    const int role_id = blockIdx.z;
+    const VtRole& R = p.role[role_id];
+    if (!R.active) return;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = base + VT_STAGES * VT_STAGE_BYTES;
+    auto full = [&](int s) { return bar_base + 8u * s; };
+    auto empty = [&](int s) { return bar_base + 8u * (VT_STAGES + s); };
+    const uint32_t acc_full = bar_base + 8u * (2 * VT_STAGES);
+    const uint32_t tmem_slot = acc_full + 8;
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slice = blockIdx.x;              // 32 hidden units
+    const int m0 = blockIdx.y * 128;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < VT_STAGES; s++) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+        mbar_init(acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(tmem_slot) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_gen;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const CUtensorMap* ah = &maps.a_hi[R.a_sel];
+            const CUtensorMap* al = &maps.a_lo[R.a_sel];
+            const CUtensorMap* bh = &maps.b_hi[role_id];
+            const CUtensorMap* bl = &maps.b_lo[role_id];
+            int s = 0, ph = 0;
+            for (int kb = 0; kb < VT_NKB; kb++) {
+                mbar_wait(empty(s), ph ^ 1);
+                mbar_expect_tx(full(s), VT_STAGE_BYTES);
+                const uint32_t st = base + s * VT_STAGE_BYTES;
+                tma_load_2d(st, ah, full(s), kb * 64, m0);
+                tma_load_2d(st + VT_A_BYTES, al, full(s), kb * 64, m0);
+                tma_load_2d(st + 2 * VT_A_BYTES, bh, full(s), kb * 64, slice * VT_N);
+                tma_load_2d(st + 2 * VT_A_BYTES + VT_B_BYTES, bl, full(s), kb * 64, slice * VT_N);
+                if (++s == VT_STAGES) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(128, VT_N);
+            int s = 0, ph = 0;
+            for (int kb = 0; kb < VT_NKB; kb++) {
+                mbar_wait(full(s), ph);
+                tc_fence_after();
+                const uint32_t a_hi = base + s * VT_STAGE_BYTES, a_lo = a_hi + VT_A_BYTES;
+                const uint32_t b_hi = a_hi + 2 * VT_A_BYTES, b_lo = b_hi + VT_B_BYTES;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    tc_mma_f16(tmem_base, make_smem_desc(a_hi + k * 32), make_smem_desc(b_hi + k * 32), idesc, !(kb == 0 && k == 0));
+                    tc_mma_f16(tmem_base, make_smem_desc(a_lo + k * 32), make_smem_desc(b_hi + k * 32), idesc, 1u);
+                    tc_mma_f16(tmem_base, make_smem_desc(a_hi + k * 32), make_smem_desc(b_lo + k * 32), idesc, 1u);
+                }
+                tc_commit(empty(s));
+                if (++s == VT_STAGES) { s = 0; ph ^= 1; }
+            }
+            tc_commit(acc_full);
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = m0 + q * 32 + lane;
+        const bool valid = row < p.L;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        const float* bias = R.bias + slice * VT_N;
+        // operands that do not depend on the accumulator are fetched before waiting on the MMA
+        const float* gi = nullptr;
+        if (valid) {
+            if (role_id == 0) gi = R.gi + (int64_t)p.codes[row] * 1536 + slice * VT_N;
+            else if (role_id == 2) gi = R.gi + (int64_t)row * 1536 + slice * VT_N;
+        }
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int i = 0; i < 4; i++) {
+            float ar[8], az[8], an[8];
+            tmem_ld8(lane_addr + 8 * i, ar);
+            tmem_ld8(lane_addr + 32 + 8 * i, az);
+            tmem_ld8(lane_addr + 64 + 8 * i, an);
+            tmem_ld_wait();
+            if (!valid) continue;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                ar[j] += bias[8 * i + j]; az[j] += bias[32 + 8 * i + j]; an[j] += bias[64 + 8 * i + j];
+            }
+            if (role_id == 1) {
+                float* o = R.out_f32 + (int64_t)row * 1536 + slice * VT_N + 8 * i;
+                *reinterpret_cast<float4*>(o) = make_float4(ar[0], ar[1], ar[2], ar[3]);
+                *reinterpret_cast<float4*>(o + 4) = make_float4(ar[4], ar[5], ar[6], ar[7]);
+                *reinterpret_cast<float4*>(o + 32) = make_float4(az[0], az[1], az[2], az[3]);
+                *reinterpret_cast<float4*>(o + 36) = make_float4(az[4], az[5], az[6], az[7]);
+                *reinterpret_cast<float4*>(o + 64) = make_float4(an[0], an[1], an[2], an[3]);
+                *reinterpret_cast<float4*>(o + 68) = make_float4(an[4], an[5], an[6], an[7]);
+                continue;
+            }
+            const int64_t hofs = (int64_t)row * 512 + slice * 32 + 8 * i;
+            float ho[8], hn[8];
+            *reinterpret_cast<float4*>(ho) = *reinterpret_cast<const float4*>(R.h_old + hofs);
+            *reinterpret_cast<float4*>(ho + 4) = *reinterpret_cast<const float4*>(R.h_old + hofs + 4);
+            __align__(16) __half hh[8], hl[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                float rr = sigmoid_acc(gi[8 * i + j] + ar[j]);
+                float zz = sigmoid_acc(gi[32 + 8 * i + j] + az[j]);
+                float nn = tanhf(gi[64 + 8 * i + j] + rr * an[j]);
+                hn[j] = (1.0f - zz) * nn + zz * ho[j];
+                hh[j] = __float2half_rn(hn[j]);
+                hl[j] = __float2half_rn(hn[j] - __half2float(hh[j]));
+            }
+            *reinterpret_cast<float4*>(R.out_f32 + hofs) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+            *reinterpret_cast<float4*>(R.out_f32 + hofs + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
+            *reinterpret_cast<uint4*>(R.out_hi + hofs) = *reinterpret_cast<const uint4*>(hh);
+            *reinterpret_cast<uint4*>(R.out_lo + hofs) = *reinterpret_cast<const uint4*>(hl);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+struct VtState {
+    VtMaps maps;
+    bool b_ok = false;
+    const void* a_ptr = nullptr;
+    int a_L = 0;
+    bool attr_set = false;
+};
+
+int make_map2d(dmp2_engine* e, CUtensorMap* m, const __half* ptr, int rows, int rows_box) {
+    uint64_t dims[2] = {512, (uint64_t)rows};
+    uint64_t str[1] = {1024};
+    uint32_t box[2] = {64, (uint32_t)rows_box};
+    int r = tc::encode_f16_map(m, ptr, 2, dims, str, box);
+    if (r != 0) return e->fail(DMP2_ERR_CUDA, "vgru: cuTensorMapEncodeTiled failed with code " + std::to_string(r));
+    return 0;
+}
+
+}  // namespace
+
+int run_vgru_tc(dmp2_engine* e, const uint8_t* msa, int N, int L, float* out, cudaStream_t st) {
+    if (!e->vt_state) e->vt_state = new VtState();
+    VtState* S = (VtState*)e->vt_state;
+    const Weights& w = e->w;
+    Workspace& ws = e->ws;
+    if (!S->attr_set) {
+        CUDA_TRY(e, cudaFuncSetAttribute(k_vgru_step, cudaFuncAttributeMaxDynamicSharedMemorySize, VT_SMEM));
+        S->attr_set = true;
+    }
+    if (!S->b_ok) {
+        for (int r = 0; r < 3; r++) {
+            TRY(make_map2d(e, &S->maps.b_hi[r], w.vt_w_hi[r], 1536, VT_N));
+            TRY(make_map2d(e, &S->maps.b_lo[r], w.vt_w_lo[r], 1536, VT_N));
+        }
+        S->b_ok = true;
+    }
+    const int64_t hsz = (int64_t)L * 512;
+    if (S->a_ptr != ws.vt_h16 || S->a_L != L) {
+        for (int b = 0; b < 4; b++) {                                   // [buffer][hi|lo][L*512]
+            TRY(make_map2d(e, &S->maps.a_hi[b], ws.vt_h16 + (2 * b) * hsz, L, 128));
+            TRY(make_map2d(e, &S->maps.a_lo[b], ws.vt_h16 + (2 * b + 1) * hsz, L, 128));
+        }
+        S->a_ptr = ws.vt_h16;
+        S->a_L = L;
+    }
+    CUDA_TRY(e, cudaMemsetAsync(ws.vg_h, 0, 4 * hsz * sizeof(float), st));
+    CUDA_TRY(e, cudaMemsetAsync(ws.vt_h16, 0, 8 * hsz * sizeof(__half), st));
+    float* hf[4] = {ws.vg_h, ws.vg_h + hsz, ws.vg_h + 2 * hsz, ws.vg_h + 3 * hsz};     // h0 ping/pong, h1 ping/pong
+    auto hi = [&](int b) { return ws.vt_h16 + (2 * b) * hsz; };
+    auto lo = [&](int b) { return ws.vt_h16 + (2 * b + 1) * hsz; };
+    float* gi1[2] = {ws.vt_gi1, ws.vt_gi1 + (int64_t)L * 1536};
+    dim3 grid(16, cdiv(L, 128), 3);
+    for (int s = 0; s < N + 2; s++) {
+        VtParams p;
+        p.L = L;
+        p.codes = msa + (int64_t)std::min(s, N - 1) * L;
+        // role 0: time t = s, h0 state before t lives in buffer (s & 1)
+        p.role[0] = {s < N, s & 1, w.vt_bias[0], w.vt_gi0, hf[s & 1], hf[(s + 1) & 1], hi((s + 1) & 1), lo((s + 1) & 1)};
+        // role 1: time t = s-1, input h0[t] = buffer (s & 1)
+        p.role[1] = {s >= 1 && s <= N, s & 1, w.vt_bias[1], nullptr, nullptr, gi1[s & 1], nullptr, nullptr};
+        // role 2: time t = s-2, h1 state before t in buffer 2 + (t & 1), gi1[t] written by launch s-1
+        const int t2 = s - 2;
+        p.role[2] = {s >= 2, 2 + (t2 & 1), w.vt_bias[2], gi1[(s - 1) & 1], hf[2 + (t2 & 1)], hf[2 + ((t2 + 1) & 1)],
+                     hi(2 + ((t2 + 1) & 1)), lo(2 + ((t2 + 1) & 1))};
+        k_vgru_step<<<grid, VT_THREADS, VT_SMEM, st>>>(S->maps, p);
+        POST_LAUNCH(e, "k_vgru_step");
+    }
+    CUDA_TRY(e, cudaMemcpyAsync(out, hf[2 + (N & 1)], hsz * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+void vgru_tc_destroy(dmp2_engine* e) {
+    if (e->vt_state) {
+        delete (VtState*)e->vt_state;
+        e->vt_state = nullptr;
+    }
+}

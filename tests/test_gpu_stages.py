@@ -209,3 +209,13 @@ def test_tensor_core_gemm_core(eng, mode, tol, m, k):
     ref = a.double() @ b.double().t()
     got = eng.gemm_tn_test(a, b, mode).cpu().double()
     assert _rel(got, ref) < tol, _rel(got, ref)
+
+
+def test_vgru_long_wavefront(eng, oracle, pf10963):
+    """N much larger than the 3-stage wavefront depth, L spanning two 128-row tiles with a ragged tail."""
+    msa = O.synth_msa_structured(pf10963, 150, 203, 5)
+    ref = oracle.vgru_last(torch.from_numpy(msa))
+    got = eng.vgru(msa).cpu()
+    assert (got - ref).abs().max() < 1e-4
+    one = eng.vgru(msa[:1]).cpu()                      # N = 1: shortest wavefront
+    assert (one - oracle.vgru_last(torch.from_numpy(msa[:1]))).abs().max() < 1e-5
