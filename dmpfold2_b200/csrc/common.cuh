@@ -111,6 +111,9 @@ struct Workspace {
     float* seqw = nullptr;         // [N]
     float* scal = nullptr;         // [8] scalars: sum w, n_eff, ridge, ...
     float* xc = nullptr;           // [21L][Npad4] centred, sqrt(w)-scaled one-hot, transposed (K = sequence axis)
+    float* xct = nullptr;          // [Npad4][n4] transposed copy (Woodbury path)
+    float* kmat = nullptr;         // [Npad64][Npad64] Gram system of the Woodbury path
+    float* wy = nullptr;           // [Npad4][n4] K^-1 X^T
     float* cov = nullptr;          // [npad][npad] covariance -> inverse in place
     float* gj_p = nullptr;         // [64][64] pivot inverse
     float* gj_r = nullptr;         // [64][npad] row panel

@@ -1,13 +1,18 @@
 // Top-8 eigenpairs of the symmetric L x L Gram-like matrix M (network.py:247-250), replacing torch.symeig.
 // Direct method, fp64 internally (the spectrum is hostile to iterative schemes: strongly indefinite,
 // lambda_9/lambda_8 up to 0.996 -- SURVEY.md section 7.2):
-//   1. Householder tridiagonalisation          2. Sturm multi-section for the 8 largest eigenvalues
-//   3. inverse iteration + Gram-Schmidt        4. back-transformation
+//   1. Householder tridiagonalisation, rows distributed cyclically over an 8-CTA cluster (resident in shared
+//      memory when they fit), the Householder vector / matrix-vector product all-gathered through distributed
+//      shared memory, two cluster barriers per column;
+//   2. Sturm multi-section (32 shifts per round) for the 8 largest eigenvalues      } CTA 0
+//   3. inverse iteration + Gram-Schmidt, 4. back-transformation                      }
 //   5. canonical sign (largest-|component| positive, lowest index wins ties), sqrt(clamp(relu(l),1e-8)) scaling.
-// v0: one CTA, matrix resident in L2.
 #include "common.cuh"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
-#define EIG_THREADS 1024
+#define EIG_THREADS 512
+#define EIG_CL 8
 
 __device__ __forceinline__ double warp_sum(double v) {
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -40,88 +45,116 @@ __device__ __forceinline__ int sturm_count(const double* d, const double* e2, in
     return cnt;
 }
 
-__global__ void __launch_bounds__(EIG_THREADS, 1)
+// rows_smem: doubles of shared memory reserved for the matrix rows (0 = rows stay in global memory A)
+// vec_smem:  1 = the inverse-iteration work vectors (32 n doubles) live in shared memory
+__global__ void __cluster_dims__(EIG_CL, 1, 1) __launch_bounds__(EIG_THREADS, 1)
 k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* __restrict__ V, double* __restrict__ wk,
-           float* __restrict__ vals_out, float* __restrict__ mds_out, float* __restrict__ vec_out) {
+           int rows_in_smem, int vec_in_smem, float* __restrict__ vals_out, float* __restrict__ mds_out,
+           float* __restrict__ vec_out) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int c = (int)cluster.block_rank();
     extern __shared__ double sm[];
-    double* sv = sm;                 // [n] householder vector
-    double* sp = sm + n;             // [n] p, then w
-    double* sd = sm + 2 * n;         // [n] diagonal of T
-    double* se = sm + 3 * n;         // [n] off-diagonal of T
-    double* se2 = sm + 4 * n;        // [n] e^2
+    double* svb = sm;                // [2][n] householder vector (ping-pong)
+    double* spb = sm + 2 * n;        // [2][n] p, then w          (ping-pong)
+    double* sd = sm + 4 * n;         // [n] diagonal of T
+    double* se = sm + 5 * n;         // [n] off-diagonal of T
+    double* se2 = sm + 6 * n;        // [n] e^2
+    double* big = sm + 7 * n;        // matrix rows during phase 1, inverse-iteration vectors afterwards
     __shared__ double red[33];
     __shared__ double lam[8];
-    __shared__ double dots[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = EIG_THREADS / 32;
-    // workspace in global: beta[n], then per-vector arrays
-    double* beta = wk;               // [n]
-    double* zs = wk + n;             // [8][n] eigenvectors of T, then of M
-    double* u0 = zs + 8 * n;         // [8][n] LU of T - lambda I (three diagonals + multipliers)
-    double* u1 = u0 + 8 * n;
-    double* u2 = u1 + 8 * n;
-    double* mu = u2 + 8 * n;
-    // swap flags share mu's sign-free storage: keep a separate array
-    double* sw = mu + 8 * n;         // [8][n] 0/1
+    // global workspace: d[n], e[n], beta[n], then the per-vector arrays when they do not fit in shared memory
+    double* gd = wk;
+    double* ge = wk + n;
+    double* beta = wk + 2 * n;
+    double* gvec = wk + 3 * n;       // [32][n]
 
-    for (int64_t i = tid; i < (int64_t)n * n; i += EIG_THREADS) A[i] = (double)M[i];
-    __syncthreads();
+    // this CTA owns rows i with i % EIG_CL == c; local row li = i / EIG_CL
+    const int nloc = (n - c + EIG_CL - 1) / EIG_CL;
+    double* rbase;
+    int64_t rstride;
+    if (rows_in_smem) { rbase = big; rstride = n; }
+    else { rbase = A + (int64_t)c * n; rstride = (int64_t)EIG_CL * n; }
+    for (int li = warp; li < nloc; li += NW) {
+        const float* src = M + (int64_t)(li * EIG_CL + c) * n;
+        double* dst = rbase + li * rstride;
+        for (int j = lane; j < n; j += 32) dst[j] = (double)src[j];
+    }
+    cluster.sync();
 
-    // ---------------- 1. Householder tridiagonalisation (full symmetric storage kept up to date) --------
+    // ---------------- 1. Householder tridiagonalisation ----------------------------------------------------
     for (int k = 0; k < n - 2; k++) {
-        const int m = n - k - 1;                     // length of the column below the diagonal
-        double part = 0.0;
-        for (int i = tid; i < m; i += EIG_THREADS) {
-            double x = A[(int64_t)(k + 1 + i) * n + k];
-            sv[i] = x;
-            part += x * x;
+        const int m = n - k - 1;                       // length of the column below the diagonal
+        const int pp = k & 1;
+        double* sv = svb + pp * n;
+        double* sp = spb + pp * n;
+        // all-gather column k (rows > k) into every CTA's sv
+        const int li0 = (k + 1 - c + EIG_CL - 1) / EIG_CL;           // first local row with global index > k
+        for (int li = li0 + tid; li < nloc; li += EIG_THREADS) {
+            const int i = li * EIG_CL + c;
+            const double x = rbase[li * rstride + k];
+#pragma unroll
+            for (int d = 0; d < EIG_CL; d++) cluster.map_shared_rank(sv, d)[i - k - 1] = x;
         }
-        double sigma = block_sum(part, red);
-        double x0 = sv[0];
-        double tail = sigma - x0 * x0;
-        if (tid == 0) sd[k] = A[(int64_t)k * n + k];
-        if (!(tail > 0.0)) {                        // column already tridiagonal
-            if (tid == 0) { se[k] = x0; beta[k] = 0.0; }
-            for (int i = tid; i < m; i += EIG_THREADS) V[(int64_t)k * n + i] = 0.0;
-            __syncthreads();
+        if (tid == 0 && (k % EIG_CL) == c) gd[k] = rbase[(k / EIG_CL) * rstride + k];
+        cluster.sync();
+        double part = 0.0;
+        for (int i = tid; i < m; i += EIG_THREADS) part += sv[i] * sv[i];
+        const double sigma = block_sum(part, red);
+        const double x0 = sv[0];
+        const double tail = sigma - x0 * x0;
+        if (!(tail > 0.0)) {                           // column already tridiagonal: no reflector
+            if (c == 0) {
+                if (tid == 0) { ge[k] = x0; beta[k] = 0.0; }
+                for (int i = tid; i < m; i += EIG_THREADS) V[(int64_t)k * n + i] = 0.0;
+            }
+            cluster.sync();                            // keep the barrier count per column uniform
             continue;
         }
-        double alpha = (x0 >= 0.0) ? -sqrt(sigma) : sqrt(sigma);
-        double v0 = x0 - alpha;
-        double bt = 2.0 / (tail + v0 * v0);
+        const double alpha = (x0 >= 0.0) ? -sqrt(sigma) : sqrt(sigma);
+        const double v0 = x0 - alpha;
+        const double bt = 2.0 / (tail + v0 * v0);
         __syncthreads();
-        if (tid == 0) { sv[0] = v0; se[k] = alpha; beta[k] = bt; }
+        if (tid == 0) sv[0] = v0;
         __syncthreads();
-        for (int i = tid; i < m; i += EIG_THREADS) V[(int64_t)k * n + i] = sv[i];
-        // p = beta * A22 v   (warp per row, lanes along the row)
-        for (int i = warp; i < m; i += NW) {
-            const double* row = A + (int64_t)(k + 1 + i) * n + (k + 1);
+        if (c == 0) {
+            if (tid == 0) { ge[k] = alpha; beta[k] = bt; }
+            for (int i = tid; i < m; i += EIG_THREADS) V[(int64_t)k * n + i] = sv[i];
+        }
+        // p = beta * A22 v for the rows this CTA owns, all-gathered into every CTA's sp
+        for (int li = li0 + warp; li < nloc; li += NW) {
+            const double* row = rbase + li * rstride + (k + 1);
             double acc = 0.0;
             for (int j = lane; j < m; j += 32) acc += row[j] * sv[j];
-            acc = warp_sum(acc);
-            if (lane == 0) sp[i] = bt * acc;
+            acc = warp_sum(acc) * bt;
+            if (lane < EIG_CL) cluster.map_shared_rank(sp, lane)[li * EIG_CL + c - k - 1] = acc;
         }
-        __syncthreads();
+        cluster.sync();
         double pv = 0.0;
         for (int i = tid; i < m; i += EIG_THREADS) pv += sp[i] * sv[i];
-        double kk = 0.5 * bt * block_sum(pv, red);
-        for (int i = tid; i < m; i += EIG_THREADS) sp[i] -= kk * sv[i];      // w
+        const double kk = 0.5 * bt * block_sum(pv, red);
+        for (int i = tid; i < m; i += EIG_THREADS) sp[i] -= kk * sv[i];      // w (each CTA keeps a full copy)
         __syncthreads();
-        for (int i = warp; i < m; i += NW) {
-            double* row = A + (int64_t)(k + 1 + i) * n + (k + 1);
+        for (int li = li0 + warp; li < nloc; li += NW) {
+            double* row = rbase + li * rstride + (k + 1);
+            const int i = li * EIG_CL + c - k - 1;
             const double vi = sv[i], wi = sp[i];
             for (int j = lane; j < m; j += 32) row[j] -= vi * sp[j] + wi * sv[j];
         }
         __syncthreads();
     }
     if (tid == 0) {
-        sd[n - 2] = A[(int64_t)(n - 2) * n + (n - 2)];
-        sd[n - 1] = A[(int64_t)(n - 1) * n + (n - 1)];
-        se[n - 2] = A[(int64_t)(n - 1) * n + (n - 2)];
-        se[n - 1] = 0.0;
+        for (int i = n - 2; i < n; i++)
+            if (i >= 0 && (i % EIG_CL) == c) gd[i] = rbase[(i / EIG_CL) * rstride + i];
+        if (((n - 1) % EIG_CL) == c) { ge[n - 2] = rbase[((n - 1) / EIG_CL) * rstride + (n - 2)]; ge[n - 1] = 0.0; }
     }
+    __threadfence();
+    cluster.sync();
+    if (c != 0) return;                                // phases 2-5 only touch global memory and CTA 0's smem
+
+    for (int i = tid; i < n; i += EIG_THREADS) { sd[i] = gd[i]; se[i] = ge[i]; se2[i] = ge[i] * ge[i]; }
     __syncthreads();
-    for (int i = tid; i < n; i += EIG_THREADS) se2[i] = se[i] * se[i];
     // Gershgorin bounds
     double lo_p = 1e300, hi_p = -1e300;
     for (int i = tid; i < n; i += EIG_THREADS) {
@@ -129,7 +162,7 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
         lo_p = fmin(lo_p, sd[i] - r);
         hi_p = fmax(hi_p, sd[i] + r);
     }
-    __shared__ double glo[EIG_THREADS / 32], ghi[EIG_THREADS / 32];
+    __shared__ double glo[NW], ghi[NW];
     for (int o = 16; o; o >>= 1) {
         lo_p = fmin(lo_p, __shfl_xor_sync(0xffffffffu, lo_p, o));
         hi_p = fmax(hi_p, __shfl_xor_sync(0xffffffffu, hi_p, o));
@@ -150,8 +183,8 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
         for (int round = 0; round < 16; round++) {
             double step = (hi - lo) / 33.0;
             double x = lo + step * (double)(lane + 1);
-            int c = sturm_count(sd, se2, n, x, tiny);
-            unsigned bal = __ballot_sync(0xffffffffu, c <= kidx);
+            int cnt = sturm_count(sd, se2, n, x, tiny);
+            unsigned bal = __ballot_sync(0xffffffffu, cnt <= kidx);
             int npre = __popc(bal);
             double x_lo = __shfl_sync(0xffffffffu, x, npre > 0 ? npre - 1 : 0);
             double x_hi = __shfl_sync(0xffffffffu, x, npre < 32 ? npre : 31);
@@ -166,6 +199,11 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
     __syncthreads();
 
     // ---------------- 3. inverse iteration on T ---------------------------------------------------------
+    double* vecs = vec_in_smem ? big : gvec;
+    double* zs = vecs;               // [8][n] eigenvectors of T, then of M
+    double* u0 = zs + 8 * n;         // [8][n] LU of T - lambda I: three diagonals of U
+    double* u1 = u0 + 8 * n;
+    double* u2 = u1 + 8 * n;
     for (int i = tid; i < 8 * n; i += EIG_THREADS) {
         int w = i / n, r = i - w * n;
         unsigned h = (unsigned)(r * 2654435761u) ^ (unsigned)((w + 1) * 40503u);
@@ -179,8 +217,8 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
             const int w = warp;
             const double l = lam[w];
             double* z = zs + w * n;
-            double *U0 = u0 + w * n, *U1 = u1 + w * n, *U2 = u2 + w * n, *MU = mu + w * n, *SW = sw + w * n;
-            // factor + forward substitution in one sweep (factor recomputed every iteration: cheap)
+            double *U0 = u0 + w * n, *U1 = u1 + w * n, *U2 = u2 + w * n;
+            // LU with partial pivoting of the tridiagonal, forward substitution in the same sweep
             double c0 = sd[0] - l, c1 = n > 1 ? se[0] : 0.0;          // current row i: (diag, super)
             double rhs = z[0];
             for (int i = 0; i < n - 1; i++) {
@@ -191,12 +229,12 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
                 if (fabs(sub) <= fabs(c0)) {
                     if (fabs(c0) < pivmin) c0 = c0 < 0 ? -pivmin : pivmin;
                     double mlt = sub / c0;
-                    U0[i] = c0; U1[i] = c1; U2[i] = 0.0; MU[i] = mlt; SW[i] = 0.0;
+                    U0[i] = c0; U1[i] = c1; U2[i] = 0.0;
                     z[i] = rhs;
                     c0 = an - mlt * c1; c1 = bn; rhs = rn - mlt * rhs;
                 } else {
                     double mlt = c0 / sub;
-                    U0[i] = sub; U1[i] = an; U2[i] = bn; MU[i] = mlt; SW[i] = 1.0;
+                    U0[i] = sub; U1[i] = an; U2[i] = bn;
                     z[i] = rn;
                     c0 = c1 - mlt * an; c1 = -mlt * bn; rhs = rhs - mlt * rn;
                 }
@@ -213,8 +251,7 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
                 z2 = z1; z1 = t;
                 zmax = fmax(zmax, fabs(t));
             }
-            // scale to avoid overflow in the dot products
-            double sc = zmax > 0 ? 1.0 / zmax : 1.0;
+            double sc = zmax > 0 ? 1.0 / zmax : 1.0;                  // avoid overflow in the dot products
             for (int i = 0; i < n; i++) z[i] *= sc;
         }
         __syncthreads();
@@ -237,7 +274,6 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
             __syncthreads();
         }
     }
-    (void)dots;
 
     // ---------------- 4. back-transform: z <- H_0 H_1 ... H_{n-3} z  (warp w owns vector w) --------------
     if (warp < 8) {
@@ -279,14 +315,24 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
 
 int run_eig_top8(dmp2_engine* e, const float* m, int L, float* vals, float* mds_scaled, float* vecs_raw, cudaStream_t st) {
     static bool attr_set = false;
-    size_t smem = (size_t)5 * L * sizeof(double);
+    constexpr size_t LIMIT = 200 * 1024;
     if (!attr_set) {
-        CUDA_TRY(e, cudaFuncSetAttribute(k_eig_top8, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CUDA_TRY(e, cudaFuncSetAttribute(k_eig_top8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LIMIT));
         attr_set = true;
     }
-    if (smem > 200 * 1024) return e->fail(DMP2_ERR_UNSUPPORTED, "eig_top8: L too large for the single-CTA solver");
+    const size_t n = (size_t)L;
+    const size_t rows = ((n + EIG_CL - 1) / EIG_CL) * n;       // doubles per CTA
+    const size_t vec = 32 * n;
+    int rows_in_smem = 0, vec_in_smem = 0;
+    size_t big = 0;
+    if ((7 * n + std::max(rows, vec)) * 8 <= LIMIT) { rows_in_smem = 1; vec_in_smem = 1; big = std::max(rows, vec); }
+    else if ((7 * n + rows) * 8 <= LIMIT) { rows_in_smem = 1; big = rows; }
+    else if ((7 * n + vec) * 8 <= LIMIT) { vec_in_smem = 1; big = vec; }
+    const size_t smem = (7 * n + big) * 8;
+    if (smem > LIMIT) return e->fail(DMP2_ERR_UNSUPPORTED, "eig_top8: L too large");
     double* V = e->ws.eig_a + (int64_t)L * L;
-    k_eig_top8<<<1, EIG_THREADS, smem, st>>>(m, L, e->ws.eig_a, V, e->ws.eig_w, vals, mds_scaled, vecs_raw);
+    k_eig_top8<<<EIG_CL, EIG_THREADS, smem, st>>>(m, L, e->ws.eig_a, V, e->ws.eig_w, rows_in_smem, vec_in_smem, vals, mds_scaled,
+                                                  vecs_raw);
     POST_LAUNCH(e, "k_eig_top8");
     return 0;
 }

@@ -237,7 +237,13 @@ int ensure_workspace(dmp2_engine* e, int L, int N) {
     TRY(wsalloc(e, &ws.xc, n * Npad));
     TRY(wsalloc(e, &ws.cov, npad * npad));
     TRY(wsalloc(e, &ws.gj_p, 4096));
-    TRY(wsalloc(e, &ws.gj_r, 64 * npad));
+    const int64_t Npad64 = (N + 63) & ~(int64_t)63, n4 = (n + 3) & ~(int64_t)3;
+    if (Npad64 < npad) {
+        TRY(wsalloc(e, &ws.xct, Npad * n4));
+        TRY(wsalloc(e, &ws.kmat, Npad64 * Npad64));
+        TRY(wsalloc(e, &ws.wy, Npad * n4));
+    }
+    TRY(wsalloc(e, &ws.gj_r, 64 * std::max(npad, Npad64)));
     TRY(wsalloc(e, &ws.x3, P));
     TRY(wsalloc(e, &ws.apc, 2 * L + 1));
     TRY(wsalloc(e, &ws.feat, P * DMP2_FEAT_LD));

@@ -93,8 +93,9 @@ __global__ void k_col_mean(const uint8_t* __restrict__ msa_t, const float* __res
 }
 
 // xc[(l*21+a)][n] = (onehot - mean) * sqrt(w_n), zero in the pad columns              (predict.py:48)
+// optionally also the transposed copy xct[n][l*21+a] (row stride n4) for the Woodbury path
 __global__ void k_center(const uint8_t* __restrict__ msa_t, const float* __restrict__ w, const float* __restrict__ mean,
-                         int N, int Npad, float* __restrict__ xc) {
+                         int N, int Npad, float* __restrict__ xc, float* __restrict__ xct, int n4) {
     int l = blockIdx.y;
     int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= Npad) return;
@@ -103,9 +104,36 @@ __global__ void k_center(const uint8_t* __restrict__ msa_t, const float* __restr
 #pragma unroll
     for (int a = 0; a < 21; a++) {
         float v = ((c == a ? 1.f : 0.f) - mean[l * 21 + a]) * sw;
-        xc[((int64_t)(l * 21 + a)) * Npad + n] = n < N ? v : 0.f;
+        v = n < N ? v : 0.f;
+        xc[((int64_t)(l * 21 + a)) * Npad + n] = v;
+        if (xct) xct[(int64_t)n * n4 + l * 21 + a] = v;
     }
 }
+
+// Woodbury epilogues:  K = X^T X + ridge*n_eff*I ;  inv = (I - X Y) / ridge
+struct GramEpilogue {
+    float* c; int64_t ld; const float* scal;
+    __device__ void operator()(int m, int n, float4 v) const {
+        float d = scal[2] * scal[1];
+        if (m == n) v.x += d;
+        if (m == n + 1) v.y += d;
+        if (m == n + 2) v.z += d;
+        if (m == n + 3) v.w += d;
+        *reinterpret_cast<float4*>(c + (int64_t)m * ld + n) = v;
+    }
+};
+struct WoodburyEpilogue {
+    float* c; int64_t ld; const float* scal;
+    __device__ void operator()(int m, int n, float4 v) const {
+        float r = 1.0f / scal[2];
+        float4 o = make_float4(-v.x * r, -v.y * r, -v.z * r, -v.w * r);
+        if (m == n) o.x += r;
+        if (m == n + 1) o.y += r;
+        if (m == n + 2) o.z += r;
+        if (m == n + 3) o.w += r;
+        *reinterpret_cast<float4*>(c + (int64_t)m * ld + n) = o;
+    }
+};
 
 // cov = xc xc^T / n_eff + ridge * I, written into the npad x npad Gauss-Jordan buffer (predict.py:50-51)
 struct CovEpilogue {
@@ -275,6 +303,26 @@ __global__ void k_feat_repack(const float* __restrict__ src, int src_ld, float* 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// in-place inverse of the SPD matrix a (npad x npad, npad % 64 == 0)
+static int gj_invert(dmp2_engine* e, float* a, int npad, cudaStream_t st) {
+    Workspace& ws = e->ws;
+    for (int k0 = 0; k0 < npad; k0 += 64) {
+        k_gj_pivot<<<1, 256, 0, st>>>(a, npad, k0, ws.gj_p);
+        POST_LAUNCH(e, "k_gj_pivot");
+        sgemm_launch<4>(64, npad, 64, LoadRowMajorK{ws.gj_p, 64}, LoadColMajorN{a + (int64_t)k0 * npad, npad},
+                        StoreRowMajor{ws.gj_r, npad, nullptr, 1.0f}, st);
+        POST_LAUNCH(e, "sgemm<gj_row>");
+        if (npad >= 2048)
+            sgemm_launch<8>(npad, npad, 64, LoadRowMajorK{a + k0, npad}, LoadColMajorN{ws.gj_r, npad}, GjUpdateEpilogue{a, npad, k0}, st);
+        else
+            sgemm_launch<4>(npad, npad, 64, LoadRowMajorK{a + k0, npad}, LoadColMajorN{ws.gj_r, npad}, GjUpdateEpilogue{a, npad, k0}, st);
+        POST_LAUNCH(e, "sgemm<gj_update>");
+        k_gj_panels<<<cdiv(npad, 8), 256, 0, st>>>(a, npad, npad, k0, ws.gj_p, ws.gj_r);
+        POST_LAUNCH(e, "k_gj_panels");
+    }
+    return 0;
+}
+
 static int prep_msa(dmp2_engine* e, const uint8_t* msa, int N, int L, cudaStream_t st) {
     int Npad = (N + 3) & ~3;
     dim3 g(cdiv(Npad, 32), cdiv(L, 32));
@@ -303,31 +351,36 @@ int run_dca(dmp2_engine* e, const uint8_t* msa, int N, int L, const float* w, fl
     }
     const int Npad = (N + 3) & ~3;
     const int n = 21 * L, npad = (n + 63) & ~63;
-    float* mean = ws.apc;               // reuse: [21L] fits? apc is 2L+1 -> use gj_r instead
-    mean = ws.gj_r;                     // [64][npad] >= 21L floats
+    float* mean = ws.gj_r;              // [64][npad] >= 21L floats, free until the Gauss-Jordan loop
     k_weight_scalars<<<1, 1024, 0, st>>>(w, N, ws.scal);
     POST_LAUNCH(e, "k_weight_scalars");
     k_col_mean<<<L, 32, 0, st>>>(ws.msa_t, w, N, Npad, ws.scal, mean);
     POST_LAUNCH(e, "k_col_mean");
-    k_center<<<dim3(cdiv(Npad, 256), L), 256, 0, st>>>(ws.msa_t, w, mean, N, Npad, ws.xc);
+    const int Npad64 = (N + 63) & ~63, n4 = (n + 3) & ~3;
+    const bool woodbury = Npad64 < npad;       // N < 21 L: invert the N x N Gram system instead (Woodbury identity)
+    if (woodbury && n4 != n) CUDA_TRY(e, cudaMemsetAsync(ws.xct, 0, (size_t)Npad * n4 * sizeof(float), st));   // pad columns
+    k_center<<<dim3(cdiv(Npad, 256), L), 256, 0, st>>>(ws.msa_t, w, mean, N, Npad, ws.xc, woodbury ? ws.xct : nullptr, n4);
     POST_LAUNCH(e, "k_center");
-    sgemm_launch<8>(n, n, Npad, LoadRowMajorK{ws.xc, Npad}, LoadRowMajorK{ws.xc, Npad}, CovEpilogue{ws.cov, npad, ws.scal}, st);
-    POST_LAUNCH(e, "sgemm<cov>");
-    if (npad != n) {
-        k_pad_identity<<<(unsigned)cdiv64((int64_t)npad * npad, 256), 256, 0, st>>>(ws.cov, n, npad);
+    if (!woodbury) {
+        sgemm_launch<8>(n, n, Npad, LoadRowMajorK{ws.xc, Npad}, LoadRowMajorK{ws.xc, Npad}, CovEpilogue{ws.cov, npad, ws.scal}, st);
+        POST_LAUNCH(e, "sgemm<cov>");
+        if (npad != n) {
+            k_pad_identity<<<(unsigned)cdiv64((int64_t)npad * npad, 256), 256, 0, st>>>(ws.cov, n, npad);
+            POST_LAUNCH(e, "k_pad_identity");
+        }
+        TRY(gj_invert(e, ws.cov, npad, st));
+    } else {
+        // cov_reg = ridge*I + X X^T / n_eff  with X = xc (21L x N)
+        // inv     = (I - X (ridge*n_eff*I_N + X^T X)^-1 X^T) / ridge
+        sgemm_launch<4>(Npad, Npad, n4, LoadRowMajorK{ws.xct, n4}, LoadRowMajorK{ws.xct, n4}, GramEpilogue{ws.kmat, Npad64, ws.scal}, st);
+        POST_LAUNCH(e, "sgemm<gram>");
+        k_pad_identity<<<(unsigned)cdiv64((int64_t)Npad64 * Npad64, 256), 256, 0, st>>>(ws.kmat, N, Npad64);
         POST_LAUNCH(e, "k_pad_identity");
-    }
-    for (int k0 = 0; k0 < npad; k0 += 64) {
-        k_gj_pivot<<<1, 256, 0, st>>>(ws.cov, npad, k0, ws.gj_p);
-        POST_LAUNCH(e, "k_gj_pivot");
-        sgemm_launch<4>(64, npad, 64, LoadRowMajorK{ws.gj_p, 64}, LoadColMajorN{ws.cov + (int64_t)k0 * npad, npad},
-                        StoreRowMajor{ws.gj_r, npad, nullptr, 1.0f}, st);
-        POST_LAUNCH(e, "sgemm<gj_row>");
-        sgemm_launch<8>(npad, npad, 64, LoadRowMajorK{ws.cov + k0, npad}, LoadColMajorN{ws.gj_r, npad},
-                        GjUpdateEpilogue{ws.cov, npad, k0}, st);
-        POST_LAUNCH(e, "sgemm<gj_update>");
-        k_gj_panels<<<cdiv(npad, 8), 256, 0, st>>>(ws.cov, npad, npad, k0, ws.gj_p, ws.gj_r);
-        POST_LAUNCH(e, "k_gj_panels");
+        TRY(gj_invert(e, ws.kmat, Npad64, st));
+        sgemm_launch<8>(Npad, n4, Npad, LoadRowMajorK{ws.kmat, Npad64}, LoadColMajorN{ws.xct, n4}, StoreRowMajor{ws.wy, n4, nullptr, 1.0f}, st);
+        POST_LAUNCH(e, "sgemm<woodbury_y>");
+        sgemm_launch<8>(n, n4, Npad, LoadRowMajorK{ws.xc, Npad}, LoadColMajorN{ws.wy, n4}, WoodburyEpilogue{ws.cov, npad, ws.scal}, st);
+        POST_LAUNCH(e, "sgemm<woodbury_inv>");
     }
     k_feat_gather<<<dim3(L, L), 128, 0, st>>>(ws.cov, npad, L, feat444, ws.x3);
     POST_LAUNCH(e, "k_feat_gather");
