@@ -71,6 +71,10 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
     double* gvec = wk + 3 * n;       // [32][n]
 
     // this CTA owns rows i with i % EIG_CL == c; local row li = i / EIG_CL
+    // phase timestamps (ns, %globaltimer) for dmp2_debug_eig_phases: start, tridiag, bisect, invit, done
+    unsigned long long* stamps = reinterpret_cast<unsigned long long*>(wk + 35 * n);
+    auto stamp = [&](int i) { if (c == 0 && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); stamps[i] = t; } };
+    stamp(0);
     const int nloc = (n - c + EIG_CL - 1) / EIG_CL;
     double* rbase;
     int64_t rstride;
@@ -152,6 +156,7 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
     __threadfence();
     cluster.sync();
     if (c != 0) return;                                // phases 2-5 only touch global memory and CTA 0's smem
+    stamp(1);
 
     for (int i = tid; i < n; i += EIG_THREADS) { sd[i] = gd[i]; se[i] = ge[i]; se2[i] = ge[i] * ge[i]; }
     __syncthreads();
@@ -198,6 +203,7 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
     }
     __syncthreads();
 
+    stamp(2);
     // ---------------- 3. inverse iteration on T ---------------------------------------------------------
     double* vecs = vec_in_smem ? big : gvec;
     double* zs = vecs;               // [8][n] eigenvectors of T, then of M
@@ -275,6 +281,7 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
         }
     }
 
+    stamp(3);
     // ---------------- 4. back-transform: z <- H_0 H_1 ... H_{n-3} z  (warp w owns vector w) --------------
     if (warp < 8) {
         double* z = zs + warp * n;
@@ -311,6 +318,8 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
         }
         if (lane == 0 && vals_out) vals_out[warp] = lf;
     }
+    __syncthreads();
+    stamp(4);
 }
 
 int run_eig_top8(dmp2_engine* e, const float* m, int L, float* vals, float* mds_scaled, float* vecs_raw, cudaStream_t st) {

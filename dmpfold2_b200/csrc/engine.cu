@@ -418,6 +418,16 @@ int dmp2_stage_times(const dmp2_engine* e, float* out_ms, int cap) {
     return n;
 }
 
+int dmp2_debug_eig_phases(dmp2_engine* e, int L, double* out_us, int cap) {
+    if (!e || !out_us || cap < 4 || !e->ws.eig_w) return DMP2_ERR_BAD_ARG;
+    TRY(check_device(e));
+    CUDA_TRY(e, cudaDeviceSynchronize());
+    unsigned long long st[5];
+    CUDA_TRY(e, cudaMemcpy(st, e->ws.eig_w + 35 * (int64_t)L, sizeof(st), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 4; i++) out_us[i] = (double)(st[i + 1] - st[i]) * 1e-3;
+    return 0;
+}
+
 int dmp2_set_profile(dmp2_engine* e, int on) {
     if (!e) return DMP2_ERR_BAD_ARG;
     TRY(check_device(e));

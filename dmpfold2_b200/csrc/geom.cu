@@ -30,57 +30,95 @@ int run_dmap(dmp2_engine* e, const float* ca, int L, float* dmap, bool clamp, cu
 }
 
 // ---------------------------------------------------------------------------------------------------
-// refine_coords: one persistent CTA, coordinates double-buffered in shared memory, S lanes per atom.
-// No L x L x 3 tensors, no autograd.
+// refine_coords: one persistent CTA, coordinates double-buffered in shared memory, S threads per atom (each
+// scans a strided share of the partners).  No L x L x 3 tensors, no autograd.  Pairs at >= 3.0 A contribute
+// exactly zero force in the reference (violate = 0), so they are skipped on the squared distance.
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024, 1) k_refine(float* __restrict__ ca, int L, int steps, int S /* pow2 <= 32 */) {
+__global__ void __launch_bounds__(1024, 1) k_refine(float* __restrict__ ca, int L, int steps, int S, int Lp) {
+    extern __shared__ float sh[];
+    float* buf[2] = {sh, sh + 3 * L};
+    float* part = sh + 6 * L;                         // [S][3][Lp] partial accelerations
+    for (int i = threadIdx.x; i < 3 * L; i += blockDim.x) sh[i] = ca[i];
+    __syncthreads();
+    const int j = threadIdx.x % Lp, sub = threadIdx.x / Lp;
+    const bool act = j < L && sub < S;
+    for (int s = 0; s < steps; s++) {
+        const float* c = buf[s & 1];
+        float* o = buf[(s & 1) ^ 1];
+        float ax = 0.f, ay = 0.f, az = 0.f, cx = 0.f, cy = 0.f, cz = 0.f;
+        if (act) {
+            cx = c[3 * j]; cy = c[3 * j + 1]; cz = c[3 * j + 2];
+            for (int i = sub; i < L; i += S) {
+                float dx = cx - c[3 * i], dy = cy - c[3 * i + 1], dz = cz - c[3 * i + 2];
+                float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                if (d2 < 9.0f) {
+                    float d = fmaxf(sqrtf(d2), 0.01f);
+                    float f = 100.0f * (3.0f - d);
+                    ax += f * (dx / d); ay += f * (dy / d); az += f * (dz / d);
+                }
+            }
+            if (S > 1) { part[(sub * 3 + 0) * Lp + j] = ax; part[(sub * 3 + 1) * Lp + j] = ay; part[(sub * 3 + 2) * Lp + j] = az; }
+        }
+        if (S > 1) __syncthreads();
+        if (act && sub == 0) {
+            for (int q = 1; q < S; q++) { ax += part[(q * 3 + 0) * Lp + j]; ay += part[(q * 3 + 1) * Lp + j]; az += part[(q * 3 + 2) * Lp + j]; }
+            if (j < L - 1) {              // bond to j+1: accels[j] += acov_j
+                float ux = c[3 * j + 3] - cx, uy = c[3 * j + 4] - cy, uz = c[3 * j + 5] - cz;
+                float d = fmaxf(sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(ux, ux), __fmul_rn(uy, uy)), __fmul_rn(uz, uz))), 0.1f);
+                float f = 100.0f * fminf(d - 3.78f, 3.0f);
+                ax += f * (ux / d); ay += f * (uy / d); az += f * (uz / d);
+            }
+            if (j > 0) {                  // bond from j-1: accels[j] -= acov_{j-1}
+                float ux = cx - c[3 * j - 3], uy = cy - c[3 * j - 2], uz = cz - c[3 * j - 1];
+                float d = fmaxf(sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(ux, ux), __fmul_rn(uy, uy)), __fmul_rn(uz, uz))), 0.1f);
+                float f = 100.0f * fminf(d - 3.78f, 3.0f);
+                ax -= f * (ux / d); ay -= f * (uy / d); az -= f * (uz / d);
+            }
+            o[3 * j] = cx + fminf(fmaxf(ax, -100.f), 100.f) * 0.001f;
+            o[3 * j + 1] = cy + fminf(fmaxf(ay, -100.f), 100.f) * 0.001f;
+            o[3 * j + 2] = cz + fminf(fmaxf(az, -100.f), 100.f) * 0.001f;
+        }
+        __syncthreads();
+    }
+    const float* c = buf[steps & 1];
+    for (int i = threadIdx.x; i < 3 * L; i += blockDim.x) ca[i] = c[i];
+}
+
+// L > 1024: several atoms per thread are not supported by the single-CTA layout above; use a simple multi-pass variant
+__global__ void __launch_bounds__(1024, 1) k_refine_large(float* __restrict__ ca, int L, int steps) {
     extern __shared__ float sh[];
     float* buf[2] = {sh, sh + 3 * L};
     for (int i = threadIdx.x; i < 3 * L; i += blockDim.x) sh[i] = ca[i];
     __syncthreads();
-    const int sub = threadIdx.x & (S - 1);
-    const int slot = threadIdx.x / S, nslots = blockDim.x / S;
     for (int s = 0; s < steps; s++) {
         const float* c = buf[s & 1];
         float* o = buf[(s & 1) ^ 1];
-        for (int jb = 0; jb < L; jb += nslots) {
-            const int j = jb + slot;
-            const bool act = j < L;
-            float ax = 0.f, ay = 0.f, az = 0.f, cx = 0.f, cy = 0.f, cz = 0.f;
-            if (act) {
-                cx = c[3 * j]; cy = c[3 * j + 1]; cz = c[3 * j + 2];
-                for (int i = sub; i < L; i += S) {
-                    float dx = cx - c[3 * i], dy = cy - c[3 * i + 1], dz = cz - c[3 * i + 2];
-                    float d = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
-                    d = fminf(fmaxf(d, 0.01f), 10.0f);
-                    if (d < 3.0f) {
-                        float f = 100.0f * (3.0f - d);
-                        ax += f * (dx / d); ay += f * (dy / d); az += f * (dz / d);
-                    }
+        for (int j = threadIdx.x; j < L; j += blockDim.x) {
+            float cx = c[3 * j], cy = c[3 * j + 1], cz = c[3 * j + 2], ax = 0.f, ay = 0.f, az = 0.f;
+            for (int i = 0; i < L; i++) {
+                float dx = cx - c[3 * i], dy = cy - c[3 * i + 1], dz = cz - c[3 * i + 2];
+                float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                if (d2 < 9.0f) {
+                    float d = fmaxf(sqrtf(d2), 0.01f);
+                    float f = 100.0f * (3.0f - d);
+                    ax += f * (dx / d); ay += f * (dy / d); az += f * (dz / d);
                 }
             }
-            for (int w = S >> 1; w; w >>= 1) {
-                ax += __shfl_xor_sync(0xffffffffu, ax, w);
-                ay += __shfl_xor_sync(0xffffffffu, ay, w);
-                az += __shfl_xor_sync(0xffffffffu, az, w);
+            if (j < L - 1) {
+                float ux = c[3 * j + 3] - cx, uy = c[3 * j + 4] - cy, uz = c[3 * j + 5] - cz;
+                float d = fmaxf(sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(ux, ux), __fmul_rn(uy, uy)), __fmul_rn(uz, uz))), 0.1f);
+                float f = 100.0f * fminf(d - 3.78f, 3.0f);
+                ax += f * (ux / d); ay += f * (uy / d); az += f * (uz / d);
             }
-            if (act && sub == 0) {
-                if (j < L - 1) {          // bond to j+1: accels[j] += acov_j
-                    float ux = c[3 * j + 3] - cx, uy = c[3 * j + 4] - cy, uz = c[3 * j + 5] - cz;
-                    float d = fmaxf(sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(ux, ux), __fmul_rn(uy, uy)), __fmul_rn(uz, uz))), 0.1f);
-                    float f = 100.0f * fminf(d - 3.78f, 3.0f);
-                    ax += f * (ux / d); ay += f * (uy / d); az += f * (uz / d);
-                }
-                if (j > 0) {              // bond from j-1: accels[j] -= acov_{j-1}
-                    float ux = cx - c[3 * j - 3], uy = cy - c[3 * j - 2], uz = cz - c[3 * j - 1];
-                    float d = fmaxf(sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(ux, ux), __fmul_rn(uy, uy)), __fmul_rn(uz, uz))), 0.1f);
-                    float f = 100.0f * fminf(d - 3.78f, 3.0f);
-                    ax -= f * (ux / d); ay -= f * (uy / d); az -= f * (uz / d);
-                }
-                o[3 * j] = cx + fminf(fmaxf(ax, -100.f), 100.f) * 0.001f;
-                o[3 * j + 1] = cy + fminf(fmaxf(ay, -100.f), 100.f) * 0.001f;
-                o[3 * j + 2] = cz + fminf(fmaxf(az, -100.f), 100.f) * 0.001f;
+            if (j > 0) {
+                float ux = cx - c[3 * j - 3], uy = cy - c[3 * j - 2], uz = cz - c[3 * j - 1];
+                float d = fmaxf(sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(ux, ux), __fmul_rn(uy, uy)), __fmul_rn(uz, uz))), 0.1f);
+                float f = 100.0f * fminf(d - 3.78f, 3.0f);
+                ax -= f * (ux / d); ay -= f * (uy / d); az -= f * (uz / d);
             }
+            o[3 * j] = cx + fminf(fmaxf(ax, -100.f), 100.f) * 0.001f;
+            o[3 * j + 1] = cy + fminf(fmaxf(ay, -100.f), 100.f) * 0.001f;
+            o[3 * j + 2] = cz + fminf(fmaxf(az, -100.f), 100.f) * 0.001f;
         }
         __syncthreads();
     }
@@ -93,13 +131,20 @@ int run_refine(dmp2_engine* e, float* ca, int L, int steps, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
         CUDA_TRY(e, cudaFuncSetAttribute(k_refine, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CUDA_TRY(e, cudaFuncSetAttribute(k_refine_large, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
     }
-    size_t smem = (size_t)6 * L * sizeof(float);
-    if (smem > 200 * 1024) return e->fail(DMP2_ERR_UNSUPPORTED, "refine: L too large");
-    int S = 32;
-    while (S > 1 && 1024 / S < L) S >>= 1;       // as many lanes per atom as fit one wave of atoms
-    k_refine<<<1, 1024, smem, st>>>(ca, L, steps, S);
+    if (L > 1024) {
+        size_t smem = (size_t)6 * L * sizeof(float);
+        if (smem > 200 * 1024) return e->fail(DMP2_ERR_UNSUPPORTED, "refine: L too large");
+        k_refine_large<<<1, 1024, smem, st>>>(ca, L, steps);
+        POST_LAUNCH(e, "k_refine_large");
+        return 0;
+    }
+    const int Lp = (L + 31) & ~31;
+    const int S = 1024 / Lp;                          // threads per atom
+    size_t smem = ((size_t)6 * L + (size_t)S * 3 * Lp) * sizeof(float);
+    k_refine<<<1, 1024, smem, st>>>(ca, L, steps, S, Lp);
     POST_LAUNCH(e, "k_refine");
     return 0;
 }

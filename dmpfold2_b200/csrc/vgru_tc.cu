@@ -22,7 +22,7 @@ constexpr int VT_B_BYTES = VT_N * 64 * 2;      // 12 KB
 constexpr int VT_STAGE_BYTES = 2 * VT_A_BYTES + 2 * VT_B_BYTES;     // 56 KB
 constexpr int VT_STAGES = 4;
 constexpr int VT_SMEM = VT_STAGES * VT_STAGE_BYTES + 1024 + 256;
-constexpr int VT_THREADS = 192;
+constexpr int VT_THREADS = 320;             // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (2 per TMEM lane quarter)
 
 struct VtMaps {
     CUtensorMap a_hi[4], a_lo[4];              // h buffers: 0,1 = h0 ping/pong, 2,3 = h1 ping/pong
@@ -128,21 +128,30 @@ __global__ void __launch_bounds__(VT_THREADS, 1) k_vgru_step(const __grid_consta
             tc_commit(acc_full);
         }
     } else {
+        // 8 epilogue warps: TMEM lane quarter q = warp % 4 (hardware rule), unit half uh = 0/1 -> 16 units per thread.
         const int q = warp & 3;
+        const int uh = (warp - 2) >> 2;
         const int row = m0 + q * 32 + lane;
         const bool valid = row < p.L;
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-        const float* bias = R.bias + slice * VT_N;
-        // operands that do not depend on the accumulator are fetched before waiting on the MMA
-        const float* gi = nullptr;
-        if (valid) {
-            if (role_id == 0) gi = R.gi + (int64_t)p.codes[row] * 1536 + slice * VT_N;
-            else if (role_id == 2) gi = R.gi + (int64_t)row * 1536 + slice * VT_N;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + uh * 16;
+        const float* bias = R.bias + slice * VT_N + uh * 16;
+        // Everything that does not depend on the accumulator is fetched BEFORE waiting on the MMA, so the
+        // global-load latency hides behind the TMA/MMA phase.
+        float gi[3][16], ho[16];
+        if (valid && role_id != 1) {
+            const float* gp = (role_id == 0 ? R.gi + (int64_t)p.codes[row] * 1536 : R.gi + (int64_t)row * 1536) + slice * VT_N + uh * 16;
+            const float* hp = R.h_old + (int64_t)row * 512 + slice * 32 + uh * 16;
+#pragma unroll
+            for (int g = 0; g < 3; g++)
+#pragma unroll
+                for (int v = 0; v < 4; v++) *reinterpret_cast<float4*>(&gi[g][4 * v]) = *reinterpret_cast<const float4*>(gp + g * 32 + 4 * v);
+#pragma unroll
+            for (int v = 0; v < 4; v++) *reinterpret_cast<float4*>(&ho[4 * v]) = *reinterpret_cast<const float4*>(hp + 4 * v);
         }
         mbar_wait(acc_full, 0);
         tc_fence_after();
-#pragma unroll 1
-        for (int i = 0; i < 4; i++) {
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
             float ar[8], az[8], an[8];
             tmem_ld8(lane_addr + 8 * i, ar);
             tmem_ld8(lane_addr + 32 + 8 * i, az);
@@ -154,7 +163,7 @@ __global__ void __launch_bounds__(VT_THREADS, 1) k_vgru_step(const __grid_consta
                 ar[j] += bias[8 * i + j]; az[j] += bias[32 + 8 * i + j]; an[j] += bias[64 + 8 * i + j];
             }
             if (role_id == 1) {
-                float* o = R.out_f32 + (int64_t)row * 1536 + slice * VT_N + 8 * i;
+                float* o = R.out_f32 + (int64_t)row * 1536 + slice * VT_N + uh * 16 + 8 * i;
                 *reinterpret_cast<float4*>(o) = make_float4(ar[0], ar[1], ar[2], ar[3]);
                 *reinterpret_cast<float4*>(o + 4) = make_float4(ar[4], ar[5], ar[6], ar[7]);
                 *reinterpret_cast<float4*>(o + 32) = make_float4(az[0], az[1], az[2], az[3]);
@@ -163,17 +172,15 @@ __global__ void __launch_bounds__(VT_THREADS, 1) k_vgru_step(const __grid_consta
                 *reinterpret_cast<float4*>(o + 68) = make_float4(an[4], an[5], an[6], an[7]);
                 continue;
             }
-            const int64_t hofs = (int64_t)row * 512 + slice * 32 + 8 * i;
-            float ho[8], hn[8];
-            *reinterpret_cast<float4*>(ho) = *reinterpret_cast<const float4*>(R.h_old + hofs);
-            *reinterpret_cast<float4*>(ho + 4) = *reinterpret_cast<const float4*>(R.h_old + hofs + 4);
+            const int64_t hofs = (int64_t)row * 512 + slice * 32 + uh * 16 + 8 * i;
+            float hn[8];
             __align__(16) __half hh[8], hl[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                float rr = sigmoid_acc(gi[8 * i + j] + ar[j]);
-                float zz = sigmoid_acc(gi[32 + 8 * i + j] + az[j]);
-                float nn = tanhf(gi[64 + 8 * i + j] + rr * an[j]);
-                hn[j] = (1.0f - zz) * nn + zz * ho[j];
+                float rr = sigmoid_acc(gi[0][8 * i + j] + ar[j]);
+                float zz = sigmoid_acc(gi[1][8 * i + j] + az[j]);
+                float nn = tanhf(gi[2][8 * i + j] + rr * an[j]);
+                hn[j] = (1.0f - zz) * nn + zz * ho[8 * i + j];
                 hh[j] = __float2half_rn(hn[j]);
                 hl[j] = __float2half_rn(hn[j] - __half2float(hh[j]));
             }

@@ -29,6 +29,7 @@ _SIGS = {
     'dmp2_set_conv_mode': (_i, [_vp, _i]),
     'dmp2_launch_count': (_i64, [_vp]),
     'dmp2_stage_times': (_i, [_vp, C.POINTER(C.c_float), _i]),
+    'dmp2_debug_eig_phases': (_i, [_vp, _i, C.POINTER(C.c_double), _i]),
     'dmp2_set_profile': (_i, [_vp, _i]),
     'dmp2_conv_profile': (_i, [_vp, C.POINTER(_i), C.POINTER(C.c_float)]),
     'dmp2_fold': (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp]),
@@ -133,6 +134,11 @@ class Engine:
         buf = (C.c_float * 8)()
         n = self.lib.dmp2_stage_times(self.h, buf, 8)
         return {STAGE_NAMES[i]: float(buf[i]) for i in range(n)}
+
+    def eig_phases(self, l: int):
+        buf = (C.c_double * 4)()
+        self._check(self.lib.dmp2_debug_eig_phases(self.h, int(l), buf, 4), 'dmp2_debug_eig_phases')
+        return dict(zip(('tridiag_us', 'bisect_us', 'invit_us', 'backtransform_us'), list(buf)))
 
     def set_profile(self, on: bool):
         self._check(self.lib.dmp2_set_profile(self.h, 1 if on else 0), 'dmp2_set_profile')

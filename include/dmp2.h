@@ -63,6 +63,10 @@ int64_t dmp2_launch_count(const dmp2_engine* e);
  * features, vgru, hgru, stem, resnet(conv+norm), head+eig, coord_gru, refine+backbone.  Returns n. */
 int dmp2_stage_times(const dmp2_engine* e, float* out_ms, int cap);
 
+/* Debug: device time (us) of the four phases of the last top-8 eigensolve at size L (tridiagonalisation,
+ * bisection, inverse iteration, back-transform); synchronises the device. */
+int dmp2_debug_eig_phases(dmp2_engine* e, int L, double* out_us, int cap);
+
 /* Roofline support: when on, a CUDA-event pair is recorded (on the launching stream) around every 5x5-conv
  * kernel launch; dmp2_conv_profile synchronises the device, returns the number of launches seen and their
  * summed device time since the last call, and resets the counters. */

@@ -1,0 +1,61 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU plumbing: round-robin target sharding without data-path
+collectives, result gathering, max-over-ranks timing."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from dmpfold2_b200 import parallel as P
+
+
+def test_round_robin_shards_partition_the_targets():
+    for n in (0, 1, 7, 256):
+        for w in (1, 2, 4, 8):
+            shards = [P.targets_for_rank(n, r, w) for r in range(w)]
+            assert sorted(t for s in shards for t in s) == list(range(n))
+            assert max(len(s) for s in shards) - min(len(s) for s in shards) <= 1
+    with pytest.raises(ValueError):
+        P.targets_for_rank(4, 2, 2)
+    assert P.world() == (0, 1)
+    assert P.max_over_ranks(3.5) == 3.5
+    assert P.fold_many([1, 2, 3], lambda t: t * 10) == [10, 20, 30]
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world_size, port, out_dir):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world_size)
+    try:
+        calls = []
+
+        def fake_fold(t):                       # stands in for Engine.fold_host: a pure function of the target
+            calls.append(t)
+            return {'target': t, 'coords': torch.full((3, 5, 3), float(t)), 'rank': rank}
+        res = P.fold_many(list(range(5)), fake_fold)
+        assert calls == P.targets_for_rank(5, rank, world_size)           # no rank folds another rank's targets
+        assert [r['target'] for r in res] == [0, 1, 2, 3, 4]
+        assert [r['rank'] for r in res] == [0, 1, 0, 1, 0]
+        assert all(float(r['coords'][0, 0, 0]) == r['target'] for r in res)
+        local = P.fold_many(list(range(5)), fake_fold, gather=False)
+        assert [x is not None for x in local] == [t % world_size == rank for t in range(5)]
+        slow = P.max_over_ranks(10.0 + rank)                             # device time = max over ranks
+        assert slow == 10.0 + world_size - 1
+        with open(os.path.join(out_dir, f'ok{rank}'), 'w') as fh:
+            fh.write('ok')
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_fold_many(tmp_path):
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.isfile(tmp_path / 'ok0') and os.path.isfile(tmp_path / 'ok1')
