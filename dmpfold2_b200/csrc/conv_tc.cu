@@ -45,7 +45,9 @@ struct TcParams {
 using namespace tc;
 
 // ---- the kernel --------------------------------------------------------------------------------------
-template <bool SPLIT>
+// CL = CTAs per cluster sharing the weight (B) stream: each CTA loads 1/CL of every B piece and multicasts it
+// to all CTAs of the cluster, so the L2 -> SM weight traffic (the dominant operand stream) drops by CL.
+template <bool SPLIT, int CL>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_conv5_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
            const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const TcParams p) {
@@ -65,15 +67,17 @@ k_conv5_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - base));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = CL > 1 ? cluster_ctarank() : 0;
+    constexpr uint16_t MC_MASK = (uint16_t)((1u << CL) - 1);
 
-    // tile coordinates
+    // tile coordinates (tiles past the end of the image are all out-of-bounds: zero loads, no stores)
     int x0 = 0, y0 = 0, m0 = 0;
     if (p.gemm) m0 = blockIdx.x * TILE_M;
     else { y0 = (blockIdx.x / p.tiles_x) * TILE_H; x0 = (blockIdx.x % p.tiles_x) * TILE_W; }
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < C::NUM_A_STAGES; s++) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
-        for (int s = 0; s < NUM_B_SLOTS; s++) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+        for (int s = 0; s < NUM_B_SLOTS; s++) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), CL); }
         mbar_init(acc_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -84,6 +88,7 @@ k_conv5_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();                  // peers' barriers must be initialised before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
 
@@ -108,7 +113,15 @@ k_conv5_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
                 for (int piece = 0; piece < C::PIECES; piece++) {
                     mbar_wait(b_empty(sb), pb ^ 1);
                     mbar_expect_tx(b_full(sb), B_BYTES);
-                    tma_load_2d(b_base + sb * B_BYTES, piece < 2 ? &map_b_hi : &map_b_lo, b_full(sb), k0, (piece & 1) * 256);
+                    const CUtensorMap* bm = piece < 2 ? &map_b_hi : &map_b_lo;
+                    const uint32_t bdst = b_base + sb * B_BYTES;
+                    const int n0 = (piece & 1) * 256;
+                    if (CL == 1) {
+                        tma_load_2d(bdst, bm, b_full(sb), k0, n0);
+                        tma_load_2d(bdst + B_BYTES / 2, bm, b_full(sb), k0, n0 + 128);
+                    } else {                                   // my half of the piece, delivered to every CTA of the cluster
+                        tma_load_2d_mc(bdst + crank * (B_BYTES / CL), bm, b_full(sb), k0, n0 + crank * (256 / CL), MC_MASK);
+                    }
                     if (++sb == NUM_B_SLOTS) { sb = 0; pb ^= 1; }
                 }
             }
@@ -136,7 +149,8 @@ k_conv5_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
                         for (int k = 0; k < KCHUNK / 16; k++)
                             tc_mma_f16(d, make_smem_desc(a_lo + k * 32), make_smem_desc(b_addr + k * 32), idesc, 1u);
                     }
-                    tc_commit(b_empty(sb));
+                    if (CL == 1) tc_commit(b_empty(sb));
+                    else tc_commit_mc(b_empty(sb), MC_MASK);   // the slot is free only when every CTA of the cluster is done with it
                     if (++sb == NUM_B_SLOTS) { sb = 0; pb ^= 1; }
                 }
                 tc_commit(a_empty(sa));
@@ -185,6 +199,7 @@ k_conv5_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();                  // no CTA may exit while a peer can still arrive on its barriers
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
@@ -213,8 +228,10 @@ int get_state(dmp2_engine* e, TcState** out) {
     }
     TcState* s = (TcState*)e->tc_state;
     if (!s->attr_set) {
-        CUDA_TRY(e, cudaFuncSetAttribute(k_conv5_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<true>::SMEM_BYTES));
-        CUDA_TRY(e, cudaFuncSetAttribute(k_conv5_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<false>::SMEM_BYTES));
+        CUDA_TRY(e, cudaFuncSetAttribute(k_conv5_tc<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<true>::SMEM_BYTES));
+        CUDA_TRY(e, cudaFuncSetAttribute(k_conv5_tc<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<false>::SMEM_BYTES));
+        CUDA_TRY(e, cudaFuncSetAttribute(k_conv5_tc<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<true>::SMEM_BYTES));
+        CUDA_TRY(e, cudaFuncSetAttribute(k_conv5_tc<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<false>::SMEM_BYTES));
         s->attr_set = true;
     }
     *out = s;
@@ -231,14 +248,24 @@ int encode_map(dmp2_engine* e, TcState*, CUtensorMap* map, const void* ptr, int 
 int weight_map(dmp2_engine* e, TcState* s, CUtensorMap* map, const __half* w, int K) {
     uint64_t dims[2] = {(uint64_t)K, 512};
     uint64_t str[1] = {(uint64_t)K * 2};
-    uint32_t box[2] = {KCHUNK, 256};
+    uint32_t box[2] = {KCHUNK, 128};          // half a 256-cout piece: the multicast unit of a 2-CTA cluster
     return encode_map(e, s, map, w, 2, dims, str, box);
 }
 
-template <bool SPLIT>
+template <bool SPLIT, int CL>
 int launch(dmp2_engine* e, const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
            const TcParams& p, int grid, cudaStream_t st) {
-    k_conv5_tc<SPLIT><<<grid, NUM_THREADS, Cfg<SPLIT>::SMEM_BYTES, st>>>(ah, al, bh, bl, p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((grid + CL - 1) / CL * CL);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = Cfg<SPLIT>::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CUDA_TRY(e, cudaLaunchKernelEx(&cfg, k_conv5_tc<SPLIT, CL>, ah, al, bh, bl, p));
     POST_LAUNCH(e, "k_conv5_tc");
     return 0;
 }
@@ -264,8 +291,12 @@ int run_conv_tc(dmp2_engine* e, int blk, const __half* xh, const __half* xl, int
     TcParams p;
     p.gemm = 0; p.L = L; p.tiles_x = cdiv(L, TILE_W); p.num_kb = 50; p.M = L * L; p.out = raw; p.bias = e->w.blk[blk].bias;
     int grid = p.tiles_x * cdiv(L, TILE_H);
-    if (mode == DMP2_CONV_TC_F16X3) return launch<true>(e, s->amap[0], s->amap[1], s->wmap[blk][0], s->wmap[blk][1], p, grid, st);
-    return launch<false>(e, s->amap[0], s->amap[1], s->wmap[blk][0], s->wmap[blk][1], p, grid, st);
+    const bool mc = e->conv_cluster != 1;
+    if (mode == DMP2_CONV_TC_F16X3)
+        return mc ? launch<true, 2>(e, s->amap[0], s->amap[1], s->wmap[blk][0], s->wmap[blk][1], p, grid, st)
+                  : launch<true, 1>(e, s->amap[0], s->amap[1], s->wmap[blk][0], s->wmap[blk][1], p, grid, st);
+    return mc ? launch<false, 2>(e, s->amap[0], s->amap[1], s->wmap[blk][0], s->wmap[blk][1], p, grid, st)
+              : launch<false, 1>(e, s->amap[0], s->amap[1], s->wmap[blk][0], s->wmap[blk][1], p, grid, st);
 }
 
 // C[M,512] = A[M,K] * B[512,K]^T through the same TMA / tcgen05 / TMEM pipeline (descriptor + pipeline self-test)
@@ -293,8 +324,8 @@ int run_gemm_tn_test(dmp2_engine* e, const float* a, const float* b, int M, int 
         TcParams p;
         p.gemm = 1; p.L = 0; p.tiles_x = 1; p.num_kb = K / KCHUNK; p.M = M; p.out = c; p.bias = nullptr;
         int grid = cdiv(M, TILE_M);
-        rc = (mode == DMP2_CONV_TC_F16X3) ? launch<true>(e, mah, mal, mbh, mbl, p, grid, st)
-                                          : launch<false>(e, mah, mal, mbh, mbl, p, grid, st);
+        rc = (mode == DMP2_CONV_TC_F16X3) ? launch<true, 1>(e, mah, mal, mbh, mbl, p, grid, st)
+                                          : launch<false, 1>(e, mah, mal, mbh, mbl, p, grid, st);
     } while (0);
     cudaStreamSynchronize(st);
     cudaFree(ah); cudaFree(al); cudaFree(bh); cudaFree(bl);

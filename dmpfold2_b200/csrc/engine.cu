@@ -383,6 +383,8 @@ int dmp2_create(dmp2_engine** out, int device, int n_tensors, const char* const*
         else if (!strcmp(mode, "f16")) e->conv_mode = DMP2_CONV_TC_F16;
         else if (!strcmp(mode, "ffma")) e->conv_mode = DMP2_CONV_FFMA;
     }
+    const char* cc = getenv("DMP2_CONV_CLUSTER");
+    if (cc && !strcmp(cc, "1")) e->conv_cluster = 1;
     const char* vm = getenv("DMP2_VGRU");
     if (vm && !strcmp(vm, "ffma")) e->vgru_mode = 1;
     *out = e;
