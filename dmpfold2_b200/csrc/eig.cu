@@ -33,16 +33,37 @@ __device__ double block_sum(double v, double* red) {
     return red[32];
 }
 
-// number of eigenvalues of the tridiagonal (d, e2 = e^2) that are < x
-__device__ __forceinline__ int sturm_count(const double* d, const double* e2, int n, double x, double tiny) {
-    double q = d[0] - x;
-    int cnt = q < 0.0;
+// Number of eigenvalues of the tridiagonal (d, e2 = e^2) that are < x: sign changes of the leading principal
+// minors p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2} (division-free Sturm sequence, rescaled against overflow;
+// a zero minor takes the sign opposite to its predecessor).  One FMA on the dependent chain per row.
+__device__ __forceinline__ int sturm_count(const double* d, const double* e2, int n, double x) {
+    const double BIG = 1.3407807929942597e154, SMALL = 7.458340731200207e-155;   // 2^512, 2^-512
+    double pm = 1.0, p = d[0] - x;
+    int cnt = p < 0.0;
+    if (p == 0.0) { p = -1e-300; cnt = 1; }
     for (int i = 1; i < n; i++) {
-        if (fabs(q) < tiny) q = q < 0.0 ? -tiny : tiny;
-        q = d[i] - x - e2[i - 1] / q;
-        cnt += q < 0.0;
+        double t = e2[i - 1] * pm;
+        double pn = fma(d[i] - x, p, -t);
+        if (pn == 0.0) pn = p > 0.0 ? -1e-300 * fabs(p) - 1e-300 : 1e-300 * fabs(p) + 1e-300;
+        cnt += (pn < 0.0) != (p < 0.0);
+        pm = p; p = pn;
+        double ap = fabs(p);
+        if (ap > BIG) { p *= SMALL; pm *= SMALL; }
+        else if (ap < SMALL) { p *= BIG; pm *= BIG; }
     }
     return cnt;
+}
+
+// one-barrier block reduction: every thread returns the same total (fixed order); `scr` holds EIG_THREADS/32 doubles
+// and must not be reused before another block-wide barrier has been passed
+__device__ __forceinline__ double block_sum1(double v, double* scr) {
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) scr[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < EIG_THREADS / 32; i++) t += scr[i];
+    return t;
 }
 
 // rows_smem: doubles of shared memory reserved for the matrix rows (0 = rows stay in global memory A)
@@ -88,12 +109,14 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
     cluster.sync();
 
     // ---------------- 1. Householder tridiagonalisation ----------------------------------------------------
+    // Per column: 2 cluster barriers (all-gather of the column, all-gather of A v) + 3 block barriers.  The first
+    // component of the Householder vector (v0) is carried in a register, so the gathered column is never patched.
+    __shared__ double scr_a[EIG_THREADS / 32], scr_b[EIG_THREADS / 32];
     for (int k = 0; k < n - 2; k++) {
         const int m = n - k - 1;                       // length of the column below the diagonal
         const int pp = k & 1;
         double* sv = svb + pp * n;
         double* sp = spb + pp * n;
-        // all-gather column k (rows > k) into every CTA's sv
         const int li0 = (k + 1 - c + EIG_CL - 1) / EIG_CL;           // first local row with global index > k
         for (int li = li0 + tid; li < nloc; li += EIG_THREADS) {
             const int i = li * EIG_CL + c;
@@ -105,7 +128,7 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
         cluster.sync();
         double part = 0.0;
         for (int i = tid; i < m; i += EIG_THREADS) part += sv[i] * sv[i];
-        const double sigma = block_sum(part, red);
+        const double sigma = block_sum1(part, scr_a);
         const double x0 = sv[0];
         const double tail = sigma - x0 * x0;
         if (!(tail > 0.0)) {                           // column already tridiagonal: no reflector
@@ -119,32 +142,32 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
         const double alpha = (x0 >= 0.0) ? -sqrt(sigma) : sqrt(sigma);
         const double v0 = x0 - alpha;
         const double bt = 2.0 / (tail + v0 * v0);
-        __syncthreads();
-        if (tid == 0) sv[0] = v0;
-        __syncthreads();
         if (c == 0) {
             if (tid == 0) { ge[k] = alpha; beta[k] = bt; }
-            for (int i = tid; i < m; i += EIG_THREADS) V[(int64_t)k * n + i] = sv[i];
+            for (int i = tid; i < m; i += EIG_THREADS) V[(int64_t)k * n + i] = i == 0 ? v0 : sv[i];
         }
         // p = beta * A22 v for the rows this CTA owns, all-gathered into every CTA's sp
         for (int li = li0 + warp; li < nloc; li += NW) {
             const double* row = rbase + li * rstride + (k + 1);
-            double acc = 0.0;
-            for (int j = lane; j < m; j += 32) acc += row[j] * sv[j];
+            double acc = lane == 0 ? row[0] * v0 : 0.0;
+            for (int j = lane == 0 ? 32 : lane; j < m; j += 32) acc += row[j] * sv[j];
             acc = warp_sum(acc) * bt;
             if (lane < EIG_CL) cluster.map_shared_rank(sp, lane)[li * EIG_CL + c - k - 1] = acc;
         }
         cluster.sync();
         double pv = 0.0;
-        for (int i = tid; i < m; i += EIG_THREADS) pv += sp[i] * sv[i];
-        const double kk = 0.5 * bt * block_sum(pv, red);
-        for (int i = tid; i < m; i += EIG_THREADS) sp[i] -= kk * sv[i];      // w (each CTA keeps a full copy)
-        __syncthreads();
+        for (int i = tid; i < m; i += EIG_THREADS) pv += sp[i] * (i == 0 ? v0 : sv[i]);
+        const double kk = 0.5 * bt * block_sum1(pv, scr_b);
+        // rank-2 update of the owned rows with w = p - kk v formed on the fly
         for (int li = li0 + warp; li < nloc; li += NW) {
             double* row = rbase + li * rstride + (k + 1);
             const int i = li * EIG_CL + c - k - 1;
-            const double vi = sv[i], wi = sp[i];
-            for (int j = lane; j < m; j += 32) row[j] -= vi * sp[j] + wi * sv[j];
+            const double vi = i == 0 ? v0 : sv[i];
+            const double wi = sp[i] - kk * vi;
+            for (int j = lane; j < m; j += 32) {
+                const double vj = j == 0 ? v0 : sv[j];
+                row[j] -= vi * (sp[j] - kk * vj) + wi * vj;
+            }
         }
         __syncthreads();
     }
@@ -177,7 +200,6 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
     double gl = glo[0], gh = ghi[0];
     for (int i = 1; i < NW; i++) { gl = fmin(gl, glo[i]); gh = fmax(gh, ghi[i]); }
     const double tnorm = fmax(fabs(gl), fabs(gh));
-    const double tiny = fmax(tnorm * 1e-20, 1e-300);
     gl -= tnorm * 1e-12 + 1e-300;
     gh += tnorm * 1e-12 + 1e-300;
 
@@ -188,7 +210,7 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
         for (int round = 0; round < 16; round++) {
             double step = (hi - lo) / 33.0;
             double x = lo + step * (double)(lane + 1);
-            int cnt = sturm_count(sd, se2, n, x, tiny);
+            int cnt = sturm_count(sd, se2, n, x);
             unsigned bal = __ballot_sync(0xffffffffu, cnt <= kidx);
             int npre = __popc(bal);
             double x_lo = __shfl_sync(0xffffffffu, x, npre > 0 ? npre - 1 : 0);
@@ -234,25 +256,27 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
                 double rn = z[i + 1];
                 if (fabs(sub) <= fabs(c0)) {
                     if (fabs(c0) < pivmin) c0 = c0 < 0 ? -pivmin : pivmin;
-                    double mlt = sub / c0;
-                    U0[i] = c0; U1[i] = c1; U2[i] = 0.0;
+                    double rc = 1.0 / c0;
+                    double mlt = sub * rc;
+                    U0[i] = rc; U1[i] = c1; U2[i] = 0.0;
                     z[i] = rhs;
                     c0 = an - mlt * c1; c1 = bn; rhs = rn - mlt * rhs;
                 } else {
-                    double mlt = c0 / sub;
-                    U0[i] = sub; U1[i] = an; U2[i] = bn;
+                    double rs = 1.0 / sub;
+                    double mlt = c0 * rs;
+                    U0[i] = rs; U1[i] = an; U2[i] = bn;
                     z[i] = rn;
                     c0 = c1 - mlt * an; c1 = -mlt * bn; rhs = rhs - mlt * rn;
                 }
             }
             if (fabs(c0) < pivmin) c0 = c0 < 0 ? -pivmin : pivmin;
-            U0[n - 1] = c0; U1[n - 1] = 0.0; U2[n - 1] = 0.0;
+            U0[n - 1] = 1.0 / c0; U1[n - 1] = 0.0; U2[n - 1] = 0.0;
             z[n - 1] = rhs;
-            // back substitution (the two previous solutions stay in registers)
+            // back substitution (U0 holds reciprocal pivots; the two previous solutions stay in registers)
             double zmax = 0.0, z1 = 0.0, z2 = 0.0;
 #pragma unroll 4
             for (int i = n - 1; i >= 0; i--) {
-                double t = (z[i] - U1[i] * z1 - U2[i] * z2) / U0[i];
+                double t = (z[i] - U1[i] * z1 - U2[i] * z2) * U0[i];
                 z[i] = t;
                 z2 = z1; z1 = t;
                 zmax = fmax(zmax, fabs(t));
@@ -261,21 +285,27 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
             for (int i = 0; i < n; i++) z[i] *= sc;
         }
         __syncthreads();
-        // modified Gram-Schmidt in ascending order + normalisation
+        // Gram-Schmidt in ascending order + normalisation: warp p < w forms <z_p, z_w>, then one fused update
+        __shared__ double dots[8];
         for (int w = 0; w < 8; w++) {
             double* z = zs + w * n;
-            for (int p = 0; p < w; p++) {
-                const double* zp = zs + p * n;
+            if (warp < w) {
+                const double* zp = zs + warp * n;
                 double a = 0.0;
-                for (int i = tid; i < n; i += EIG_THREADS) a += zp[i] * z[i];
-                double dt = block_sum(a, red);
-                for (int i = tid; i < n; i += EIG_THREADS) z[i] -= dt * zp[i];
-                __syncthreads();
+                for (int i = lane; i < n; i += 32) a += zp[i] * z[i];
+                a = warp_sum(a);
+                if (lane == 0) dots[warp] = a;
             }
-            double a = 0.0;
-            for (int i = tid; i < n; i += EIG_THREADS) a += z[i] * z[i];
-            double nr = block_sum(a, red);
-            double inv = nr > 0 ? 1.0 / sqrt(nr) : 0.0;
+            __syncthreads();
+            double nrm = 0.0;
+            for (int i = tid; i < n; i += EIG_THREADS) {
+                double v = z[i];
+                for (int p = 0; p < w; p++) v -= dots[p] * zs[p * n + i];
+                z[i] = v;
+                nrm += v * v;
+            }
+            const double nr = block_sum1(nrm, (w & 1) ? scr_a : scr_b);
+            const double inv = nr > 0 ? 1.0 / sqrt(nr) : 0.0;
             for (int i = tid; i < n; i += EIG_THREADS) z[i] *= inv;
             __syncthreads();
         }
@@ -283,7 +313,36 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
 
     stamp(3);
     // ---------------- 4. back-transform: z <- H_0 H_1 ... H_{n-3} z  (warp w owns vector w) --------------
-    if (warp < 8) {
+    // Reflectors are staged 16 at a time into shared memory by all warps (one L2 round trip per block instead of
+    // one per reflector) when the work vectors live in shared memory; otherwise they are read in place.
+    if (vec_in_smem) {
+        double* stage = u0;                            // 24 n doubles, free after the inverse iteration
+        for (int khi = n - 3; khi >= 0; khi -= 16) {
+            const int klo = khi - 15 > 0 ? khi - 15 : 0;
+            for (int r = warp; r <= khi - klo; r += NW) {
+                const int k = klo + r, m = n - k - 1;
+                const double* v = V + (int64_t)k * n;
+                for (int i = lane; i < m; i += 32) stage[r * n + i] = v[i];
+            }
+            __syncthreads();
+            if (warp < 8) {
+                double* z = zs + warp * n;
+                for (int k = khi; k >= klo; k--) {
+                    const double bt = beta[k];
+                    if (bt == 0.0) continue;
+                    const int m = n - k - 1;
+                    const double* v = stage + (k - klo) * n;
+                    double* zz = z + k + 1;
+                    double a = 0.0;
+                    for (int i = lane; i < m; i += 32) a += v[i] * zz[i];
+                    a = warp_sum(a) * bt;
+                    for (int i = lane; i < m; i += 32) zz[i] -= a * v[i];
+                    __syncwarp();
+                }
+            }
+            __syncthreads();
+        }
+    } else if (warp < 8) {
         double* z = zs + warp * n;
         for (int k = n - 3; k >= 0; k--) {
             const double bt = beta[k];
@@ -297,6 +356,9 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
             for (int i = lane; i < m; i += 32) zz[i] -= a * v[i];
             __syncwarp();
         }
+    }
+    if (warp < 8) {
+        double* z = zs + warp * n;
         // ---------------- 5. canonical sign + MDS scaling -------------------------------------------------
         double best = -1.0; int bi = 0;
         for (int i = lane; i < n; i += 32) {
