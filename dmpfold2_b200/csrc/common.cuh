@@ -66,6 +66,8 @@ struct ResBlockW {
     float* w_f32;            // [512][25][128]  (cout, tap=ky*5+kx, cin)  fp32, for the FFMA path
     __half* w_hi;            // same layout, fp16 high part
     __half* w_lo;            // fp16 residual  (w - float(w_hi))
+    uint8_t* w8_w;           // e5m2 of w * 2^-8   (FP8 correction term x_lo * w)
+    uint8_t* w8_lo;          // e5m2 of w_lo * 2^4 (FP8 correction term x_hi * w_lo)
     float* bias;             // [512]
     float* gamma;            // [128]
     float* beta;             // [128]
@@ -136,6 +138,8 @@ struct Workspace {
     float* x = nullptr;            // [L*L][128] residual stream fp32 (NHWC)
     __half* xh = nullptr;          // [L*L][128] fp16 high part of x
     __half* xl = nullptr;          // [L*L][128] fp16 low part
+    uint8_t* x8lo = nullptr;       // [L*L][128] e4m3 of x_lo * 2^8
+    uint8_t* x8hi = nullptr;       // [L*L][128] e4m3 of x_hi * 2^-4
     double* stat_part = nullptr;   // [nparts][256] partial sums
     float* norm_ss = nullptr;      // [256] per-channel scale, shift
     unsigned int* ticket = nullptr;
@@ -158,7 +162,7 @@ struct Workspace {
 struct dmp2_engine {
     int device = 0;
     int num_sms = 148;
-    int conv_mode = DMP2_CONV_TC_F16X3;
+    int conv_mode = DMP2_CONV_TC_F16F8;
     int64_t launches = 0;
     int status = 0;
     std::string err;
@@ -203,12 +207,13 @@ int run_stem_base(dmp2_engine* e, const float* mat1d_t, const float* feat444, in
 int run_stem_update(dmp2_engine* e, const float* dmap, int L, cudaStream_t st);   // -> ws.x (+ xh, xl)
 int run_conv_ffma(dmp2_engine* e, int blk, const float* x, int L, float* raw, cudaStream_t st);
 int run_norm_gate(dmp2_engine* e, int blk, const float* raw, float* x, int L, bool stem, cudaStream_t st);
-int run_split_half(dmp2_engine* e, const float* x, int64_t n, __half* hi, __half* lo, cudaStream_t st);
+int run_split_half(dmp2_engine* e, const float* x, int64_t n, __half* hi, __half* lo, uint8_t* x8lo, uint8_t* x8hi, cudaStream_t st);
 int run_resblock(dmp2_engine* e, int blk, int L, cudaStream_t st);                // ws.x -> ws.x
 int run_head(dmp2_engine* e, const float* x, int L, float* head2, cudaStream_t st);
 int run_head_post(dmp2_engine* e, const float* head2, int L, float* conf, float* mmat, cudaStream_t st);
 // conv_tc.cu
-int run_conv_tc(dmp2_engine* e, int blk, const __half* xh, const __half* xl, int L, float* raw, int mode, cudaStream_t st);
+int run_conv_tc(dmp2_engine* e, int blk, const __half* xh, const __half* xl, const uint8_t* x8lo, const uint8_t* x8hi, int L,
+                float* raw, int mode, cudaStream_t st);
 int run_gemm_tn_test(dmp2_engine* e, const float* a, const float* b, int M, int N, int K, int mode, float* c, cudaStream_t st);
 void conv_tc_destroy(dmp2_engine* e);
 // eig.cu

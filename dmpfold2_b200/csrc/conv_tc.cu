@@ -2,12 +2,17 @@
 // implicit GEMM on the 5th-generation tensor cores:  M = L*L pixels, N = 512 output channels, K = 25 taps x 128.
 //
 //   TMA (cp.async.bulk.tensor, 128B swizzle, out-of-bounds zero fill = the pad-2 border)
-//     -> shared-memory rings (A: shifted 8x16-pixel patch x 64 channels; B: 256 couts x 64 channels)
-//     -> tcgen05.mma kind::f16, M=128 N=256 K=16, fp32 accumulators in TMEM (128 lanes x 512 columns = all of it)
+//     -> shared-memory rings (A: shifted 8x16-pixel patch; B: 256-cout weight pieces, multicast across a cluster)
+//     -> tcgen05.mma, M=128 N=256, fp32 accumulators in TMEM (128 lanes x 512 columns = all of it)
 //     -> epilogue warps: tcgen05.ld -> + bias -> max over 4 consecutive couts -> NHWC fp32 store.
 //
-// Precision modes: F16X3 feeds hi+lo fp16 splits of both operands and issues hi*hi + lo*hi + hi*lo
-// (~22-bit effective mantissas, fp32-equivalent for the 1e-3 A parity bar); F16 issues hi*hi only.
+// Precision modes (x = x_hi + x_lo, w = w_hi + w_lo are fp16 hi/lo splits of the fp32 operands):
+//   F16    x_hi*w_hi                                   1 MMA  per algorithmic MAC   (fast, ~1e-3 A drift)
+//   F16X3  x_hi*w_hi + x_lo*w_hi + x_hi*w_lo (all fp16) 3 MMAs                       (fp32-equivalent)
+//   F16F8  x_hi*w_hi in fp16 + the two correction terms in FP8 (e4m3 activations x e5m2 weights, kind::f8f6f4,
+//          twice the fp16 rate): the corrections are ~2^-11 of the main term, so 2-3 mantissa bits suffice.
+//          Fixed power-of-two pre-scales keep the fp8 operands in range and cancel in the product:
+//          (x_lo*2^8)(w*2^-8) and (x_hi*2^-4)(w_lo*2^4).  2 MMA-equivalents per MAC.
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue
 // (a warp may only touch TMEM lanes 32*(warp%4)..+31).
@@ -18,25 +23,35 @@ namespace {
 
 constexpr int TILE_M = 128;               // pixels per CTA (8 rows x 16 columns)
 constexpr int TILE_H = 8, TILE_W = 16;
-constexpr int KCHUNK = 64;                // channels per k-block = one 128-byte swizzle row of fp16
-constexpr int A_BYTES = TILE_M * KCHUNK * 2;          // 16 KB
-constexpr int B_BYTES = 256 * KCHUNK * 2;             // 32 KB: 256 couts x 64 cin
+constexpr int KCHUNK = 64;                // fp16 channels per 128-byte swizzle row
+constexpr int A_BYTES = TILE_M * 128;     // 16 KB: 128 pixels x 128 bytes (64 fp16 or 128 fp8 channels)
+constexpr int B_BYTES = 256 * 128;        // 32 KB: one B piece = 256 couts x 128 bytes
+constexpr int BQ_ROWS = 64;               // TMA granule of a B piece: a quarter (multicast unit for clusters up to 4)
+constexpr int BQ_BYTES = BQ_ROWS * 128;
 constexpr int NUM_B_SLOTS = 5;
 constexpr int NUM_THREADS = 192;
+enum { M_F16 = 0, M_F16X3 = 1, M_F16F8 = 2 };
 
-template <bool SPLIT>
+template <int MODE>
 struct Cfg {
-    static constexpr int A_STAGE_BYTES = SPLIT ? 2 * A_BYTES : A_BYTES;
-    static constexpr int NUM_A_STAGES = SPLIT ? 2 : 4;
-    static constexpr int PIECES = SPLIT ? 4 : 2;      // B pieces per k-block: (hi,n0) (hi,n1) [(lo,n0) (lo,n1)]
+    static constexpr int A_STAGE_BYTES = MODE == M_F16 ? A_BYTES : 2 * A_BYTES;
+    static constexpr int NUM_A_STAGES = MODE == M_F16 ? 4 : 2;
+    static constexpr int PIECES = MODE == M_F16 ? 2 : 4;      // B pieces per k-block
     static constexpr int SMEM_BYTES = NUM_A_STAGES * A_STAGE_BYTES + NUM_B_SLOTS * B_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct ConvMaps {
+    CUtensorMap a_hi, a_lo;              // fp16 activations  [L][L][128]
+    CUtensorMap a8_lo, a8_hi;            // e4m3: x_lo * 2^8, x_hi * 2^-4
+    CUtensorMap b_hi, b_lo;              // fp16 weights [512][3200]
+    CUtensorMap b8_w, b8_lo;             // e5m2: w * 2^-8, w_lo * 2^4
 };
 
 struct TcParams {
     int gemm;            // 0 = conv (3-D activation map, taps), 1 = plain GEMM test (rows x K)
     int L;               // conv: image side
     int tiles_x;         // conv: tiles per image row
-    int num_kb;          // k-blocks: conv 50 (25 taps x 2 chunks), gemm K/64
+    int num_kb;          // k-blocks: conv 50, gemm K/64
     int M;               // gemm: rows
     float* out;          // conv: raw [L*L][128]; gemm: C [M][512]
     const float* bias;   // conv: [512]
@@ -44,14 +59,24 @@ struct TcParams {
 
 using namespace tc;
 
+__device__ __forceinline__ void tc_mma_f8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// kind::f8f6f4 instruction descriptor: A = e4m3 (0), B = e5m2 (1), fp32 accumulate, K-major, M x N
+__device__ __forceinline__ uint32_t make_idesc_f8(int m, int n) {
+    return (1u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
 // ---- the kernel --------------------------------------------------------------------------------------
 // CL = CTAs per cluster sharing the weight (B) stream: each CTA loads 1/CL of every B piece and multicasts it
 // to all CTAs of the cluster, so the L2 -> SM weight traffic (the dominant operand stream) drops by CL.
-template <bool SPLIT, int CL>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-k_conv5_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-           const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const TcParams p) {
-    using C = Cfg<SPLIT>;
+template <int MODE, int CL>
+__global__ void __launch_bounds__(NUM_THREADS, 1) k_conv5_tc(const __grid_constant__ ConvMaps maps, const TcParams p) {
+    using C = Cfg<MODE>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // 128B swizzle needs 1024-byte alignment
     const uint32_t a_base = base;
@@ -97,30 +122,51 @@ k_conv5_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
         if (lane == 0) {
             int sa = 0, pa = 0, sb = 0, pb = 0;
             for (int kb = 0; kb < p.num_kb; kb++) {
-                int c0, c1, c2;
-                if (p.gemm) { c0 = kb * KCHUNK; c1 = m0; c2 = 0; }
+                // ---- A stage
+                const int tap = kb >> 1, sub = kb & 1;
+                int c1, c2;
+                if (p.gemm) { c1 = m0; c2 = 0; }
                 else {
-                    int tap = kb >> 1, kc = kb & 1;
-                    int dy = tap / 5, dx = tap - dy * 5;
-                    c0 = kc * KCHUNK; c1 = x0 + dx - 2; c2 = y0 + dy - 2;
+                    const int dy = tap / 5, dx = tap - dy * 5;
+                    c1 = x0 + dx - 2; c2 = y0 + dy - 2;
                 }
                 mbar_wait(a_empty(sa), pa ^ 1);
                 mbar_expect_tx(a_full(sa), C::A_STAGE_BYTES);
-                tma_load_3d(a_base + sa * C::A_STAGE_BYTES, &map_a_hi, a_full(sa), c0, c1, c2);
-                if (SPLIT) tma_load_3d(a_base + sa * C::A_STAGE_BYTES + A_BYTES, &map_a_lo, a_full(sa), c0, c1, c2);
+                const uint32_t ast = a_base + sa * C::A_STAGE_BYTES;
+                if (MODE == M_F16) {
+                    tma_load_3d(ast, &maps.a_hi, a_full(sa), p.gemm ? kb * KCHUNK : sub * KCHUNK, c1, c2);
+                } else if (MODE == M_F16X3) {
+                    const int c0 = p.gemm ? kb * KCHUNK : sub * KCHUNK;
+                    tma_load_3d(ast, &maps.a_hi, a_full(sa), c0, c1, c2);
+                    tma_load_3d(ast + A_BYTES, &maps.a_lo, a_full(sa), c0, c1, c2);
+                } else if (sub == 0) {                         // F16F8: both fp16 channel chunks of x_hi
+                    tma_load_3d(ast, &maps.a_hi, a_full(sa), 0, c1, c2);
+                    tma_load_3d(ast + A_BYTES, &maps.a_hi, a_full(sa), KCHUNK, c1, c2);
+                } else {                                       // F16F8: the two fp8 correction operands (128 channels each)
+                    tma_load_3d(ast, &maps.a8_lo, a_full(sa), 0, c1, c2);
+                    tma_load_3d(ast + A_BYTES, &maps.a8_hi, a_full(sa), 0, c1, c2);
+                }
                 if (++sa == C::NUM_A_STAGES) { sa = 0; pa ^= 1; }
-                const int k0 = kb * KCHUNK;               // weights are [512][K] with k = tap*128 + c = kb*64 + ...
+                // ---- B pieces
                 for (int piece = 0; piece < C::PIECES; piece++) {
+                    const CUtensorMap* bm;
+                    int k0;                                    // element offset along K of the weight row
+                    if (MODE == M_F16F8) {
+                        if (sub == 0) { bm = &maps.b_hi; k0 = tap * 128 + (piece >> 1) * KCHUNK; }
+                        else { bm = (piece >> 1) ? &maps.b8_lo : &maps.b8_w; k0 = tap * 128; }
+                    } else {
+                        bm = piece < 2 ? &maps.b_hi : &maps.b_lo;
+                        k0 = kb * KCHUNK;                      // weights are [512][K] with k = tap*128 + c = kb*64 + ...
+                    }
+                    const int n0 = (piece & 1) * 256;
                     mbar_wait(b_empty(sb), pb ^ 1);
                     mbar_expect_tx(b_full(sb), B_BYTES);
-                    const CUtensorMap* bm = piece < 2 ? &map_b_hi : &map_b_lo;
                     const uint32_t bdst = b_base + sb * B_BYTES;
-                    const int n0 = (piece & 1) * 256;
-                    if (CL == 1) {
-                        tma_load_2d(bdst, bm, b_full(sb), k0, n0);
-                        tma_load_2d(bdst + B_BYTES / 2, bm, b_full(sb), k0, n0 + 128);
-                    } else {                                   // my half of the piece, delivered to every CTA of the cluster
-                        tma_load_2d_mc(bdst + crank * (B_BYTES / CL), bm, b_full(sb), k0, n0 + crank * (256 / CL), MC_MASK);
+#pragma unroll
+                    for (int i = 0; i < 4 / CL; i++) {         // my quarters of the piece, delivered to every CTA of the cluster
+                        const int qd = crank * (4 / CL) + i;
+                        if (CL == 1) tma_load_2d(bdst + qd * BQ_BYTES, bm, b_full(sb), k0, n0 + qd * BQ_ROWS);
+                        else tma_load_2d_mc(bdst + qd * BQ_BYTES, bm, b_full(sb), k0, n0 + qd * BQ_ROWS, MC_MASK);
                     }
                     if (++sb == NUM_B_SLOTS) { sb = 0; pb ^= 1; }
                 }
@@ -130,24 +176,40 @@ k_conv5_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
         // ===================== MMA issuer =====================
         if (lane == 0) {
             const uint32_t idesc = make_idesc(128, 256);
+            const uint32_t idesc8 = make_idesc_f8(128, 256);
             int sa = 0, pa = 0, sb = 0, pb = 0;
             for (int kb = 0; kb < p.num_kb; kb++) {
+                const int sub = kb & 1;
                 mbar_wait(a_full(sa), pa);
-                const uint32_t a_hi = a_base + sa * C::A_STAGE_BYTES;
-                const uint32_t a_lo = a_hi + A_BYTES;
+                const uint32_t a0 = a_base + sa * C::A_STAGE_BYTES;
+                const uint32_t a1 = a0 + A_BYTES;
                 for (int piece = 0; piece < C::PIECES; piece++) {
                     mbar_wait(b_full(sb), pb);
                     tc_fence_after();
                     const uint32_t b_addr = b_base + sb * B_BYTES;
                     const uint32_t d = tmem_base + (uint32_t)(piece & 1) * 256u;
-                    const bool first = (kb == 0) && (piece < 2);          // first touch of this accumulator half
+                    if (MODE == M_F16F8) {
+                        const uint32_t a = (piece >> 1) ? a1 : a0;
+                        if (sub == 0) {
+                            const bool first = (kb == 0) && (piece < 2);
 #pragma unroll
-                    for (int k = 0; k < KCHUNK / 16; k++)
-                        tc_mma_f16(d, make_smem_desc(a_hi + k * 32), make_smem_desc(b_addr + k * 32), idesc, !(first && k == 0));
-                    if (SPLIT && piece < 2) {                              // lo(A) x hi(B)
+                            for (int k = 0; k < 4; k++)
+                                tc_mma_f16(d, make_smem_desc(a + k * 32), make_smem_desc(b_addr + k * 32), idesc, !(first && k == 0));
+                        } else {
 #pragma unroll
-                        for (int k = 0; k < KCHUNK / 16; k++)
-                            tc_mma_f16(d, make_smem_desc(a_lo + k * 32), make_smem_desc(b_addr + k * 32), idesc, 1u);
+                            for (int k = 0; k < 4; k++)        // K = 32 fp8 elements = 32 bytes per MMA
+                                tc_mma_f8(d, make_smem_desc(a + k * 32), make_smem_desc(b_addr + k * 32), idesc8, 1u);
+                        }
+                    } else {
+                        const bool first = (kb == 0) && (piece < 2);          // first touch of this accumulator half
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                            tc_mma_f16(d, make_smem_desc(a0 + k * 32), make_smem_desc(b_addr + k * 32), idesc, !(first && k == 0));
+                        if (MODE == M_F16X3 && piece < 2) {                    // lo(A) x hi(B)
+#pragma unroll
+                            for (int k = 0; k < 4; k++)
+                                tc_mma_f16(d, make_smem_desc(a1 + k * 32), make_smem_desc(b_addr + k * 32), idesc, 1u);
+                        }
                     }
                     if (CL == 1) tc_commit(b_empty(sb));
                     else tc_commit_mc(b_empty(sb), MC_MASK);   // the slot is free only when every CTA of the cluster is done with it
@@ -208,101 +270,115 @@ k_conv5_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
 
 // ---- host side: tensor maps -----------------------------------------------------------------------------
 struct TcState {
-    CUtensorMap wmap[DMP2_NBLOCKS][2];
+    CUtensorMap wmap[DMP2_NBLOCKS][4];               // b_hi, b_lo, b8_w, b8_lo
     bool wmap_ok[DMP2_NBLOCKS] = {false};
-    CUtensorMap amap[2];
-    const void* amap_ptr[2] = {nullptr, nullptr};
+    CUtensorMap amap[4];                             // a_hi, a_lo, a8_lo, a8_hi
+    const void* amap_ptr = nullptr;
     int amap_L = 0;
     bool attr_set = false;
-    std::vector<void*> test_allocs;
 };
+
+template <int MODE, int CL>
+int set_attr(dmp2_engine* e) {
+    CUDA_TRY(e, cudaFuncSetAttribute(k_conv5_tc<MODE, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<MODE>::SMEM_BYTES));
+    return 0;
+}
 
 int get_state(dmp2_engine* e, TcState** out) {
     if (!e->tc_state) {
-        TcState* s = new TcState();
-        if (!tc::get_encode_fn()) {
-            delete s;
-            return e->fail(DMP2_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
-        }
-        e->tc_state = s;
+        if (!tc::get_encode_fn()) return e->fail(DMP2_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+        e->tc_state = new TcState();
     }
     TcState* s = (TcState*)e->tc_state;
     if (!s->attr_set) {
-        CUDA_TRY(e, cudaFuncSetAttribute(k_conv5_tc<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<true>::SMEM_BYTES));
-        CUDA_TRY(e, cudaFuncSetAttribute(k_conv5_tc<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<false>::SMEM_BYTES));
-        CUDA_TRY(e, cudaFuncSetAttribute(k_conv5_tc<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<true>::SMEM_BYTES));
-        CUDA_TRY(e, cudaFuncSetAttribute(k_conv5_tc<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<false>::SMEM_BYTES));
+        TRY((set_attr<M_F16, 1>(e))); TRY((set_attr<M_F16, 2>(e))); TRY((set_attr<M_F16, 4>(e)));
+        TRY((set_attr<M_F16X3, 1>(e))); TRY((set_attr<M_F16X3, 2>(e))); TRY((set_attr<M_F16X3, 4>(e)));
+        TRY((set_attr<M_F16F8, 1>(e))); TRY((set_attr<M_F16F8, 2>(e))); TRY((set_attr<M_F16F8, 4>(e)));
         s->attr_set = true;
     }
     *out = s;
     return 0;
 }
 
-int encode_map(dmp2_engine* e, TcState*, CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims,
-               const uint64_t* strides_bytes, const uint32_t* box) {
-    int r = tc::encode_f16_map(map, ptr, rank, dims, strides_bytes, box);
+int encode(dmp2_engine* e, CUtensorMap* map, const void* ptr, int elem_bytes, int rank, const uint64_t* dims,
+           const uint64_t* strides_bytes, const uint32_t* box) {
+    int r = tc::encode_map(map, ptr, elem_bytes, rank, dims, strides_bytes, box);
     if (r != 0) return e->fail(DMP2_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string(r));
     return 0;
 }
 
-int weight_map(dmp2_engine* e, TcState* s, CUtensorMap* map, const __half* w, int K) {
+// weights [512][K] (K contiguous), box = one 128-byte swizzle row x 64 couts
+int weight_map(dmp2_engine* e, CUtensorMap* map, const void* w, int K, int elem_bytes) {
     uint64_t dims[2] = {(uint64_t)K, 512};
-    uint64_t str[1] = {(uint64_t)K * 2};
-    uint32_t box[2] = {KCHUNK, 128};          // half a 256-cout piece: the multicast unit of a 2-CTA cluster
-    return encode_map(e, s, map, w, 2, dims, str, box);
+    uint64_t str[1] = {(uint64_t)K * elem_bytes};
+    uint32_t box[2] = {(uint32_t)(128 / elem_bytes), BQ_ROWS};
+    return encode(e, map, w, elem_bytes, 2, dims, str, box);
 }
 
-template <bool SPLIT, int CL>
-int launch(dmp2_engine* e, const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
-           const TcParams& p, int grid, cudaStream_t st) {
+template <int MODE, int CL>
+int launch(dmp2_engine* e, const ConvMaps& maps, const TcParams& p, int grid, cudaStream_t st) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((grid + CL - 1) / CL * CL);
     cfg.blockDim = dim3(NUM_THREADS);
-    cfg.dynamicSmemBytes = Cfg<SPLIT>::SMEM_BYTES;
+    cfg.dynamicSmemBytes = Cfg<MODE>::SMEM_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    CUDA_TRY(e, cudaLaunchKernelEx(&cfg, k_conv5_tc<SPLIT, CL>, ah, al, bh, bl, p));
+    CUDA_TRY(e, cudaLaunchKernelEx(&cfg, k_conv5_tc<MODE, CL>, maps, p));
     POST_LAUNCH(e, "k_conv5_tc");
     return 0;
 }
 
+template <int MODE>
+int launch_cl(dmp2_engine* e, int cl, const ConvMaps& maps, const TcParams& p, int grid, cudaStream_t st) {
+    if (cl == 4) return launch<MODE, 4>(e, maps, p, grid, st);
+    if (cl == 2) return launch<MODE, 2>(e, maps, p, grid, st);
+    return launch<MODE, 1>(e, maps, p, grid, st);
+}
+
 }  // namespace
 
-int run_conv_tc(dmp2_engine* e, int blk, const __half* xh, const __half* xl, int L, float* raw, int mode, cudaStream_t st) {
+int run_conv_tc(dmp2_engine* e, int blk, const __half* xh, const __half* xl, const uint8_t* x8lo, const uint8_t* x8hi, int L,
+                float* raw, int mode, cudaStream_t st) {
     TcState* s;
     TRY(get_state(e, &s));
+    const ResBlockW& bw = e->w.blk[blk];
     if (!s->wmap_ok[blk]) {
-        TRY(weight_map(e, s, &s->wmap[blk][0], e->w.blk[blk].w_hi, 3200));
-        TRY(weight_map(e, s, &s->wmap[blk][1], e->w.blk[blk].w_lo, 3200));
+        TRY(weight_map(e, &s->wmap[blk][0], bw.w_hi, 3200, 2));
+        TRY(weight_map(e, &s->wmap[blk][1], bw.w_lo, 3200, 2));
+        TRY(weight_map(e, &s->wmap[blk][2], bw.w8_w, 3200, 1));
+        TRY(weight_map(e, &s->wmap[blk][3], bw.w8_lo, 3200, 1));
         s->wmap_ok[blk] = true;
     }
-    if (s->amap_ptr[0] != xh || s->amap_ptr[1] != xl || s->amap_L != L) {
+    if (s->amap_ptr != xh || s->amap_L != L) {
         uint64_t dims[3] = {128, (uint64_t)L, (uint64_t)L};
-        uint64_t str[2] = {256, (uint64_t)L * 256};
-        uint32_t box[3] = {KCHUNK, TILE_W, TILE_H};
-        TRY(encode_map(e, s, &s->amap[0], xh, 3, dims, str, box));
-        TRY(encode_map(e, s, &s->amap[1], xl, 3, dims, str, box));
-        s->amap_ptr[0] = xh; s->amap_ptr[1] = xl; s->amap_L = L;
+        uint64_t str16[2] = {256, (uint64_t)L * 256}, str8[2] = {128, (uint64_t)L * 128};
+        uint32_t box16[3] = {KCHUNK, TILE_W, TILE_H}, box8[3] = {128, TILE_W, TILE_H};
+        TRY(encode(e, &s->amap[0], xh, 2, 3, dims, str16, box16));
+        TRY(encode(e, &s->amap[1], xl, 2, 3, dims, str16, box16));
+        TRY(encode(e, &s->amap[2], x8lo, 1, 3, dims, str8, box8));
+        TRY(encode(e, &s->amap[3], x8hi, 1, 3, dims, str8, box8));
+        s->amap_ptr = xh; s->amap_L = L;
     }
+    ConvMaps maps;
+    maps.a_hi = s->amap[0]; maps.a_lo = s->amap[1]; maps.a8_lo = s->amap[2]; maps.a8_hi = s->amap[3];
+    maps.b_hi = s->wmap[blk][0]; maps.b_lo = s->wmap[blk][1]; maps.b8_w = s->wmap[blk][2]; maps.b8_lo = s->wmap[blk][3];
     TcParams p;
-    p.gemm = 0; p.L = L; p.tiles_x = cdiv(L, TILE_W); p.num_kb = 50; p.M = L * L; p.out = raw; p.bias = e->w.blk[blk].bias;
-    int grid = p.tiles_x * cdiv(L, TILE_H);
-    const bool mc = e->conv_cluster != 1;
-    if (mode == DMP2_CONV_TC_F16X3)
-        return mc ? launch<true, 2>(e, s->amap[0], s->amap[1], s->wmap[blk][0], s->wmap[blk][1], p, grid, st)
-                  : launch<true, 1>(e, s->amap[0], s->amap[1], s->wmap[blk][0], s->wmap[blk][1], p, grid, st);
-    return mc ? launch<false, 2>(e, s->amap[0], s->amap[1], s->wmap[blk][0], s->wmap[blk][1], p, grid, st)
-              : launch<false, 1>(e, s->amap[0], s->amap[1], s->wmap[blk][0], s->wmap[blk][1], p, grid, st);
+    p.gemm = 0; p.L = L; p.tiles_x = cdiv(L, TILE_W); p.num_kb = 50; p.M = L * L; p.out = raw; p.bias = bw.bias;
+    const int grid = p.tiles_x * cdiv(L, TILE_H);
+    const int cl = e->conv_cluster;
+    if (mode == DMP2_CONV_TC_F16X3) return launch_cl<M_F16X3>(e, cl, maps, p, grid, st);
+    if (mode == DMP2_CONV_TC_F16F8) return launch_cl<M_F16F8>(e, cl, maps, p, grid, st);
+    return launch_cl<M_F16>(e, cl, maps, p, grid, st);
 }
 
 // C[M,512] = A[M,K] * B[512,K]^T through the same TMA / tcgen05 / TMEM pipeline (descriptor + pipeline self-test)
 int run_gemm_tn_test(dmp2_engine* e, const float* a, const float* b, int M, int N, int K, int mode, float* c, cudaStream_t st) {
     if (N != 512 || K % KCHUNK != 0 || M < 1) return e->fail(DMP2_ERR_BAD_ARG, "gemm_tn_test: need N == 512 and K % 64 == 0");
-    if (mode != DMP2_CONV_TC_F16X3 && mode != DMP2_CONV_TC_F16) return e->fail(DMP2_ERR_BAD_ARG, "gemm_tn_test: tensor-core modes only");
+    if (mode != DMP2_CONV_TC_F16X3 && mode != DMP2_CONV_TC_F16) return e->fail(DMP2_ERR_BAD_ARG, "gemm_tn_test: f16 / f16x3 modes only");
     TcState* s;
     TRY(get_state(e, &s));
     __half *ah, *al, *bh, *bl;
@@ -311,21 +387,21 @@ int run_gemm_tn_test(dmp2_engine* e, const float* a, const float* b, int M, int 
     CUDA_TRY(e, cudaMalloc(&bh, nb * 2)); CUDA_TRY(e, cudaMalloc(&bl, nb * 2));
     int rc = 0;
     do {
-        if ((rc = run_split_half(e, a, na, ah, al, st))) break;
-        if ((rc = run_split_half(e, b, nb, bh, bl, st))) break;
-        CUtensorMap mah, mal, mbh, mbl;
+        if ((rc = run_split_half(e, a, na, ah, al, nullptr, nullptr, st))) break;
+        if ((rc = run_split_half(e, b, nb, bh, bl, nullptr, nullptr, st))) break;
+        ConvMaps maps;
         uint64_t dims[3] = {(uint64_t)K, (uint64_t)M, 1};
         uint64_t str[2] = {(uint64_t)K * 2, (uint64_t)K * 2 * (uint64_t)M};
         uint32_t box[3] = {KCHUNK, TILE_M, 1};
-        if ((rc = encode_map(e, s, &mah, ah, 3, dims, str, box))) break;
-        if ((rc = encode_map(e, s, &mal, al, 3, dims, str, box))) break;
-        if ((rc = weight_map(e, s, &mbh, bh, K))) break;
-        if ((rc = weight_map(e, s, &mbl, bl, K))) break;
+        if ((rc = encode(e, &maps.a_hi, ah, 2, 3, dims, str, box))) break;
+        if ((rc = encode(e, &maps.a_lo, al, 2, 3, dims, str, box))) break;
+        if ((rc = weight_map(e, &maps.b_hi, bh, K, 2))) break;
+        if ((rc = weight_map(e, &maps.b_lo, bl, K, 2))) break;
+        maps.a8_lo = maps.a_hi; maps.a8_hi = maps.a_hi; maps.b8_w = maps.b_hi; maps.b8_lo = maps.b_hi;    // unused in these modes
         TcParams p;
         p.gemm = 1; p.L = 0; p.tiles_x = 1; p.num_kb = K / KCHUNK; p.M = M; p.out = c; p.bias = nullptr;
         int grid = cdiv(M, TILE_M);
-        rc = (mode == DMP2_CONV_TC_F16X3) ? launch<true, 1>(e, mah, mal, mbh, mbl, p, grid, st)
-                                          : launch<false, 1>(e, mah, mal, mbh, mbl, p, grid, st);
+        rc = (mode == DMP2_CONV_TC_F16X3) ? launch<M_F16X3, 1>(e, maps, p, grid, st) : launch<M_F16, 1>(e, maps, p, grid, st);
     } while (0);
     cudaStreamSynchronize(st);
     cudaFree(ah); cudaFree(al); cudaFree(bh); cudaFree(bl);

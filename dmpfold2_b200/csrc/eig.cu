@@ -11,7 +11,7 @@
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
-#define EIG_THREADS 512
+#define EIG_THREADS 1024
 #define EIG_CL 8
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -41,6 +41,7 @@ __device__ __forceinline__ int sturm_count(const double* d, const double* e2, in
     double pm = 1.0, p = d[0] - x;
     int cnt = p < 0.0;
     if (p == 0.0) { p = -1e-300; cnt = 1; }
+#pragma unroll 8
     for (int i = 1; i < n; i++) {
         double t = e2[i - 1] * pm;
         double pn = fma(d[i] - x, p, -t);
@@ -149,9 +150,12 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
         // p = beta * A22 v for the rows this CTA owns, all-gathered into every CTA's sp
         for (int li = li0 + warp; li < nloc; li += NW) {
             const double* row = rbase + li * rstride + (k + 1);
-            double acc = lane == 0 ? row[0] * v0 : 0.0;
-            for (int j = lane == 0 ? 32 : lane; j < m; j += 32) acc += row[j] * sv[j];
-            acc = warp_sum(acc) * bt;
+            double acc = lane == 0 ? row[0] * v0 : 0.0, acc2 = 0.0;
+            int j = lane == 0 ? 32 : lane;
+#pragma unroll 2
+            for (; j + 32 < m; j += 64) { acc += row[j] * sv[j]; acc2 += row[j + 32] * sv[j + 32]; }
+            if (j < m) acc += row[j] * sv[j];
+            acc = warp_sum(acc + acc2) * bt;
             if (lane < EIG_CL) cluster.map_shared_rank(sp, lane)[li * EIG_CL + c - k - 1] = acc;
         }
         cluster.sync();
@@ -164,6 +168,7 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
             const int i = li * EIG_CL + c - k - 1;
             const double vi = i == 0 ? v0 : sv[i];
             const double wi = sp[i] - kk * vi;
+#pragma unroll 4
             for (int j = lane; j < m; j += 32) {
                 const double vj = j == 0 ? v0 : sv[j];
                 row[j] -= vi * (sp[j] - kk * vj) + wi * vj;
@@ -249,11 +254,15 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
             // LU with partial pivoting of the tridiagonal, forward substitution in the same sweep
             double c0 = sd[0] - l, c1 = n > 1 ? se[0] : 0.0;          // current row i: (diag, super)
             double rhs = z[0];
+            double nx_sub = se[0], nx_d = n > 1 ? sd[1] : 0.0, nx_b = n > 2 ? se[1] : 0.0, nx_r = n > 1 ? z[1] : 0.0;
             for (int i = 0; i < n - 1; i++) {
-                double sub = se[i];                                     // T[i+1][i]
-                double an = sd[i + 1] - l;                              // T[i+1][i+1]
-                double bn = (i + 2 < n) ? se[i + 1] : 0.0;              // T[i+1][i+2]
-                double rn = z[i + 1];
+                const double sub = nx_sub;                              // T[i+1][i]
+                const double an = nx_d - l;                             // T[i+1][i+1]
+                const double bn = nx_b;                                 // T[i+1][i+2]
+                const double rn = nx_r;
+                if (i + 2 < n) {                                        // operands of the next row, off the dependent chain
+                    nx_sub = se[i + 1]; nx_d = sd[i + 2]; nx_b = (i + 3 < n) ? se[i + 2] : 0.0; nx_r = z[i + 2];
+                }
                 if (fabs(sub) <= fabs(c0)) {
                     if (fabs(c0) < pivmin) c0 = c0 < 0 ? -pivmin : pivmin;
                     double rc = 1.0 / c0;
@@ -333,10 +342,14 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
                     const int m = n - k - 1;
                     const double* v = stage + (k - klo) * n;
                     double* zz = z + k + 1;
-                    double a = 0.0;
-                    for (int i = lane; i < m; i += 32) a += v[i] * zz[i];
-                    a = warp_sum(a) * bt;
-                    for (int i = lane; i < m; i += 32) zz[i] -= a * v[i];
+                    double a = 0.0, a2 = 0.0;
+                    int i = lane;
+#pragma unroll 2
+                    for (; i + 32 < m; i += 64) { a += v[i] * zz[i]; a2 += v[i + 32] * zz[i + 32]; }
+                    if (i < m) a += v[i] * zz[i];
+                    a = warp_sum(a + a2) * bt;
+#pragma unroll 4
+                    for (i = lane; i < m; i += 32) zz[i] -= a * v[i];
                     __syncwarp();
                 }
             }

@@ -1,5 +1,6 @@
 // Engine lifetime, weight repacking, workspace, the fold orchestration and the C ABI (include/dmp2.h).
 #include "common.cuh"
+#include <cuda_fp8.h>
 #include <math.h>
 #include <string.h>
 #include <algorithm>
@@ -163,6 +164,7 @@ static int load_weights(dmp2_engine* e, HostSD& sd) {
         ResBlockW& bw = w.blk[k];
         std::vector<float> wf((size_t)512 * 3200);
         std::vector<__half> wh(wf.size()), wl(wf.size());
+        std::vector<uint8_t> w8w(wf.size()), w8l(wf.size());
         for (int o = 0; o < 512; o++)
             for (int c = 0; c < 128; c++)
                 for (int t = 0; t < 25; t++) {
@@ -171,7 +173,10 @@ static int load_weights(dmp2_engine* e, HostSD& sd) {
                     wf[d] = v;
                     __half h = __float2half_rn(v);
                     wh[d] = h;
-                    wl[d] = __float2half_rn(v - __half2float(h));
+                    float lo = v - __half2float(h);
+                    wl[d] = __float2half_rn(lo);
+                    w8w[d] = (uint8_t)__nv_cvt_float_to_fp8(v * (1.0f / 256.0f), __NV_SATFINITE, __NV_E5M2);
+                    w8l[d] = (uint8_t)__nv_cvt_float_to_fp8(lo * 16.0f, __NV_SATFINITE, __NV_E5M2);
                 }
         // cSE gate: global-average-pool of an affine InstanceNorm output is exactly beta (network.py:32,:50)
         std::vector<float> gate(128);
@@ -187,6 +192,7 @@ static int load_weights(dmp2_engine* e, HostSD& sd) {
             gate[c] = 1.0f / (1.0f + expf(-a));
         }
         TRY(upload(e, wf, &bw.w_f32)); TRY(upload(e, wh, &bw.w_hi)); TRY(upload(e, wl, &bw.w_lo));
+        TRY(upload(e, w8w, &bw.w8_w)); TRY(upload(e, w8l, &bw.w8_lo));
         TRY(upload_raw(e, cb, 512, &bw.bias)); TRY(upload_raw(e, g, 128, &bw.gamma)); TRY(upload_raw(e, b, 128, &bw.beta));
         TRY(upload(e, gate, &bw.gate_c)); TRY(upload_raw(e, sw, 128, &bw.sse_w));
         bw.sse_b = sb[0];
@@ -261,6 +267,8 @@ int ensure_workspace(dmp2_engine* e, int L, int N) {
     TRY(wsalloc(e, &ws.x, P * 128));
     TRY(wsalloc(e, &ws.xh, P * 128));
     TRY(wsalloc(e, &ws.xl, P * 128));
+    TRY(wsalloc(e, &ws.x8lo, P * 128));
+    TRY(wsalloc(e, &ws.x8hi, P * 128));
     TRY(wsalloc(e, &ws.stat_part, (int64_t)e->num_sms * 4 * 256));
     TRY(wsalloc(e, &ws.norm_ss, 256));
     TRY(wsalloc(e, &ws.ticket, 4));
@@ -382,9 +390,10 @@ int dmp2_create(dmp2_engine** out, int device, int n_tensors, const char* const*
         if (!strcmp(mode, "f16x3")) e->conv_mode = DMP2_CONV_TC_F16X3;
         else if (!strcmp(mode, "f16")) e->conv_mode = DMP2_CONV_TC_F16;
         else if (!strcmp(mode, "ffma")) e->conv_mode = DMP2_CONV_FFMA;
+        else if (!strcmp(mode, "f16f8")) e->conv_mode = DMP2_CONV_TC_F16F8;
     }
     const char* cc = getenv("DMP2_CONV_CLUSTER");
-    if (cc && !strcmp(cc, "1")) e->conv_cluster = 1;
+    if (cc && (!strcmp(cc, "1") || !strcmp(cc, "2") || !strcmp(cc, "4"))) e->conv_cluster = atoi(cc);
     const char* vm = getenv("DMP2_VGRU");
     if (vm && !strcmp(vm, "ffma")) e->vgru_mode = 1;
     *out = e;
@@ -407,7 +416,7 @@ void dmp2_destroy(dmp2_engine* e) {
 const char* dmp2_last_error(const dmp2_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
 
 int dmp2_set_conv_mode(dmp2_engine* e, int mode) {
-    if (!e || mode < 0 || mode > 2) return DMP2_ERR_BAD_ARG;
+    if (!e || mode < 0 || mode > 3) return DMP2_ERR_BAD_ARG;
     e->conv_mode = mode;
     return 0;
 }
@@ -522,8 +531,8 @@ int dmp2_conv5_maxout(dmp2_engine* e, int block, const float* x_nhwc_dev, int L,
     STAGE_PROLOGUE(L, 1);
     if (block < 1 || block > DMP2_NBLOCKS) return e->fail(DMP2_ERR_BAD_ARG, "conv5_maxout: block must be 1..16");
     if (e->conv_mode == DMP2_CONV_FFMA) return run_conv_ffma(e, block - 1, x_nhwc_dev, L, out_nhwc_dev, st);
-    TRY(run_split_half(e, x_nhwc_dev, (int64_t)L * L * 128, e->ws.xh, e->ws.xl, st));
-    return run_conv_tc(e, block - 1, e->ws.xh, e->ws.xl, L, out_nhwc_dev, e->conv_mode, st);
+    TRY(run_split_half(e, x_nhwc_dev, (int64_t)L * L * 128, e->ws.xh, e->ws.xl, e->ws.x8lo, e->ws.x8hi, st));
+    return run_conv_tc(e, block - 1, e->ws.xh, e->ws.xl, e->ws.x8lo, e->ws.x8hi, L, out_nhwc_dev, e->conv_mode, st);
 }
 
 int dmp2_resblock(dmp2_engine* e, int block, const float* x_nhwc_dev, int L, float* out_nhwc_dev, void* stream) {
@@ -531,7 +540,7 @@ int dmp2_resblock(dmp2_engine* e, int block, const float* x_nhwc_dev, int L, flo
     if (block < 1 || block > DMP2_NBLOCKS) return e->fail(DMP2_ERR_BAD_ARG, "resblock: block must be 1..16");
     const int64_t n = (int64_t)L * L * 128;
     CUDA_TRY(e, cudaMemcpyAsync(e->ws.x, x_nhwc_dev, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    TRY(run_split_half(e, e->ws.x, n, e->ws.xh, e->ws.xl, st));
+    TRY(run_split_half(e, e->ws.x, n, e->ws.xh, e->ws.xl, e->ws.x8lo, e->ws.x8hi, st));
     TRY(run_resblock(e, block - 1, L, st));
     CUDA_TRY(e, cudaMemcpyAsync(out_nhwc_dev, e->ws.x, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
     return 0;

@@ -3,6 +3,14 @@
 // Activations are NHWC: pixel p = i*L + j, 128 channels contiguous.
 #include "common.cuh"
 #include "sgemm.cuh"
+#include <cuda_fp8.h>
+
+// x -> fp16 hi, fp16 lo, and the two pre-scaled e4m3 copies used by the FP8 correction terms of the conv
+__device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float d) {
+    uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E4M3);
+    uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(c, d), __NV_SATFINITE, __NV_E4M3);
+    return lo | (hi << 16);
+}
 
 // ---------------------------------------------------------------------------------------------------
 // Stem.  The 955-channel input (512 outer-product + 441 DCA + 1 APC + 1 distance map) is never built:
@@ -117,7 +125,8 @@ __global__ void __launch_bounds__(512) k_in_stats(const float* __restrict__ raw,
 __global__ void __launch_bounds__(256) k_norm_gate(const float* __restrict__ raw, const float* __restrict__ norm,
                                                    const float* __restrict__ beta, const float* __restrict__ gate_c,
                                                    const float* __restrict__ sse_w, float sse_b, int stem, int64_t npix,
-                                                   float* __restrict__ x, __half* __restrict__ xh, __half* __restrict__ xl) {
+                                                   float* __restrict__ x, __half* __restrict__ xh, __half* __restrict__ xl,
+                                                   uint8_t* __restrict__ x8lo, uint8_t* __restrict__ x8hi) {
     const int lane = threadIdx.x & 31;
     const int c = lane * 4;
     const float4 mean = *reinterpret_cast<const float4*>(norm + c);
@@ -152,20 +161,27 @@ __global__ void __launch_bounds__(256) k_norm_gate(const float* __restrict__ raw
         lv.x = *reinterpret_cast<uint32_t*>(&l01); lv.y = *reinterpret_cast<uint32_t*>(&l23);
         *reinterpret_cast<uint2*>(xh + p * 128 + c) = hv;
         *reinterpret_cast<uint2*>(xl + p * 128 + c) = lv;
+        *reinterpret_cast<uint32_t*>(x8lo + p * 128 + c) =
+            pack_e4m3x4((o.x - f01.x) * 256.f, (o.y - f01.y) * 256.f, (o.z - f23.x) * 256.f, (o.w - f23.y) * 256.f);
+        *reinterpret_cast<uint32_t*>(x8hi + p * 128 + c) = pack_e4m3x4(f01.x * 0.0625f, f01.y * 0.0625f, f23.x * 0.0625f, f23.y * 0.0625f);
     }
 }
 
-__global__ void k_split_half(const float* __restrict__ x, int64_t n, __half* __restrict__ hi, __half* __restrict__ lo) {
+__global__ void k_split_half(const float* __restrict__ x, int64_t n, __half* __restrict__ hi, __half* __restrict__ lo,
+                             uint8_t* __restrict__ x8lo, uint8_t* __restrict__ x8hi) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float v = x[i];
     __half h = __float2half_rn(v);
+    float hf = __half2float(h);
     hi[i] = h;
-    lo[i] = __float2half_rn(v - __half2float(h));
+    lo[i] = __float2half_rn(v - hf);
+    if (x8lo) x8lo[i] = (uint8_t)__nv_cvt_float_to_fp8((v - hf) * 256.f, __NV_SATFINITE, __NV_E4M3);
+    if (x8hi) x8hi[i] = (uint8_t)__nv_cvt_float_to_fp8(hf * 0.0625f, __NV_SATFINITE, __NV_E4M3);
 }
 
-int run_split_half(dmp2_engine* e, const float* x, int64_t n, __half* hi, __half* lo, cudaStream_t st) {
-    k_split_half<<<(unsigned)cdiv64(n, 256), 256, 0, st>>>(x, n, hi, lo);
+int run_split_half(dmp2_engine* e, const float* x, int64_t n, __half* hi, __half* lo, uint8_t* x8lo, uint8_t* x8hi, cudaStream_t st) {
+    k_split_half<<<(unsigned)cdiv64(n, 256), 256, 0, st>>>(x, n, hi, lo, x8lo, x8hi);
     POST_LAUNCH(e, "k_split_half");
     return 0;
 }
@@ -190,7 +206,7 @@ int run_norm_gate(dmp2_engine* e, int blk, const float* raw, float* x, int L, bo
     int agrid = (int)std::min<int64_t>(cdiv64(npix, 8), (int64_t)e->num_sms * 8);
     k_norm_gate<<<agrid, 256, 0, st>>>(raw, ws.norm_ss, beta, stem ? nullptr : e->w.blk[blk].gate_c,
                                        stem ? nullptr : e->w.blk[blk].sse_w, stem ? 0.f : e->w.blk[blk].sse_b, stem ? 1 : 0,
-                                       npix, x, ws.xh, ws.xl);
+                                       npix, x, ws.xh, ws.xl, ws.x8lo, ws.x8hi);
     POST_LAUNCH(e, "k_norm_gate");
     return 0;
 }
@@ -232,7 +248,7 @@ int run_resblock(dmp2_engine* e, int blk, int L, cudaStream_t st) {
     const bool prof = e->profile && e->prof_used + 2 <= e->prof_ev.size();
     if (prof) cudaEventRecord(e->prof_ev[e->prof_used], st);
     if (e->conv_mode == DMP2_CONV_FFMA) TRY(run_conv_ffma(e, blk, ws.x, L, ws.raw, st));
-    else TRY(run_conv_tc(e, blk, ws.xh, ws.xl, L, ws.raw, e->conv_mode, st));
+    else TRY(run_conv_tc(e, blk, ws.xh, ws.xl, ws.x8lo, ws.x8hi, L, ws.raw, e->conv_mode, st));
     if (prof) { cudaEventRecord(e->prof_ev[e->prof_used + 1], st); e->prof_used += 2; }
     return run_norm_gate(e, blk, ws.raw, ws.x, L, false, st);
 }

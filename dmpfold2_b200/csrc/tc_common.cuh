@@ -122,18 +122,23 @@ inline EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// fp16 tensor, dims[0] contiguous, 128B swizzle, zero OOB fill.  Returns a CUresult (0 = ok, -1 = no entry point).
-inline int encode_f16_map(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                          const uint32_t* box) {
+// Tiled tensor map, dims[0] contiguous, 128B swizzle, zero OOB fill; elem_bytes 2 = fp16, 1 = 8-bit (fp8 bytes).
+// Returns a CUresult (0 = ok, -1 = no entry point).
+inline int encode_map(CUtensorMap* map, const void* ptr, int elem_bytes, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return -1;
     cuuint64_t gdim[3], gstr[2];
     cuuint32_t bx[3], estr[3] = {1, 1, 1};
     for (int i = 0; i < rank; i++) { gdim[i] = dims[i]; bx[i] = box[i]; }
     for (int i = 0; i < rank - 1; i++) gstr[i] = strides_bytes[i];
-    return (int)fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gdim, gstr, bx, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return (int)fn(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, (cuuint32_t)rank,
+                   const_cast<void*>(ptr), gdim, gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+inline int encode_f16_map(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                          const uint32_t* box) {
+    return encode_map(map, ptr, 2, rank, dims, strides_bytes, box);
 }
 
 }  // namespace tc

@@ -43,7 +43,9 @@ typedef enum {
 typedef enum {
     DMP2_CONV_TC_F16X3 = 0, /* tcgen05, fp16 hi+lo split of both operands, 3 MMAs, fp32 accumulate (parity mode) */
     DMP2_CONV_TC_F16 = 1,   /* tcgen05, single fp16 MMA, fp32 accumulate (fast mode; ~1e-3 A drift)              */
-    DMP2_CONV_FFMA = 2      /* CUDA-core fp32 implicit GEMM (validation path for the tensor-core kernels)        */
+    DMP2_CONV_FFMA = 2,     /* CUDA-core fp32 implicit GEMM (validation path for the tensor-core kernels)        */
+    DMP2_CONV_TC_F16F8 = 3  /* tcgen05, fp16 main term + the two hi/lo correction terms in FP8 (e4m3 x e5m2): 2 MMA-
+                               equivalents per MAC, error ~2^-14 relative; the default                            */
 } dmp2_conv_mode;
 
 /* ---- lifetime ------------------------------------------------------------------------------------ */

@@ -28,13 +28,14 @@ def _check(coords, conf, g, tol=TOL_RMSD):
     assert coords.shape == g['coords'].shape and np.isfinite(coords).all()
     rmsd = O.kabsch_rmsd(coords[:, 1], g['coords'][:, 1])
     rmsd_all = O.kabsch_rmsd(coords.reshape(-1, 3), g['coords'].reshape(-1, 3))
+    print(f'CA-RMSD {rmsd:.2e} A, all-atom {rmsd_all:.2e} A, max|dconf| {np.abs(conf - g["confs"]).max():.2e}')
     assert rmsd <= tol and rmsd_all <= 2 * tol, (rmsd, rmsd_all)
     assert np.abs(conf - g['confs']).max() < 2e-3
     return rmsd
 
 
 @needs_weights
-@pytest.mark.parametrize('mode', ['ffma', 'f16x3'])
+@pytest.mark.parametrize('mode', ['ffma', 'f16x3', 'f16f8'])
 @pytest.mark.parametrize('n,m', [(0, 0), (2, 20), (10, 100)])
 def test_pf10963_matches_reference(eng, pf10963, mode, n, m):
     g = np.load(os.path.join(GOLDEN, f'pf10963_n{n}_m{m}.npz'))
@@ -59,11 +60,12 @@ def test_template_and_single_sequence(eng, pf10963, tmp_path):
     _check(coords, conf, g1)
 
 
+@pytest.mark.parametrize('mode', ['f16x3', 'f16f8'])
 @pytest.mark.parametrize('l,n,seed', [(57, 40, 1), (164, 96, 2)])
-def test_structured_synthetic_vs_oracle(eng, oracle, pf10963, l, n, seed):
+def test_structured_synthetic_vs_oracle(eng, oracle, pf10963, l, n, seed, mode):
     msa = O.synth_msa_structured(pf10963, l, n, seed)
     ref_c, ref_f = oracle.fold(msa, iterations=1, minsteps=10)
-    eng.set_conv_mode('f16x3')
+    eng.set_conv_mode(mode)
     coords, conf = eng.fold_host(msa, None, 1, 10)
     _check(coords, conf, {'coords': ref_c.numpy(), 'confs': ref_f.numpy()})
 

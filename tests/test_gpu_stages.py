@@ -81,7 +81,7 @@ def _conv_ref(oracle, block, x_nchw):
     return y.view(1, 128, 4, y.shape[2], y.shape[3]).max(dim=2)[0]
 
 
-@pytest.mark.parametrize('mode,tol', [('ffma', 2e-5), ('f16x3', 2e-5), ('f16', 3e-3)])
+@pytest.mark.parametrize('mode,tol', [('ffma', 2e-5), ('f16x3', 2e-5), ('f16f8', 3e-4), ('f16', 3e-3)])
 @pytest.mark.parametrize('l', [16, 27, 82])
 def test_conv5_maxout(eng, oracle, mode, tol, l):
     g = torch.Generator().manual_seed(100 + l)
@@ -96,7 +96,7 @@ def test_conv5_maxout(eng, oracle, mode, tol, l):
         eng.set_conv_mode('ffma')
 
 
-@pytest.mark.parametrize('mode,tol', [('ffma', 5e-5), ('f16x3', 5e-5)])
+@pytest.mark.parametrize('mode,tol', [('ffma', 5e-5), ('f16x3', 5e-5), ('f16f8', 5e-4)])
 def test_resblock(eng, oracle, mode, tol):
     g = torch.Generator().manual_seed(21)
     x = torch.randn(1, 128, 33, 33, generator=g) * 2
@@ -120,7 +120,7 @@ def test_cse_gate_is_the_weights_only_constant(oracle):
 
 
 @needs_weights
-@pytest.mark.parametrize('mode,tol', [('ffma', 1e-3), ('f16x3', 1e-3)])
+@pytest.mark.parametrize('mode,tol', [('ffma', 1e-3), ('f16x3', 1e-3), ('f16f8', 2e-3)])
 def test_resnet_pass_teacher_forced(eng, oracle, pf10963, mode, tol):
     taps = {}
     oracle.fold(pf10963, iterations=0, minsteps=0, taps=taps)
