@@ -169,6 +169,8 @@ struct dmp2_engine {
     Weights w;
     std::vector<void*> weight_allocs;
     Workspace ws;
+    cudaStream_t side = nullptr;     // MSA features run here, concurrently with the vgru on the caller's stream
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev[16];
     bool ev_ok = false;
     float stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};

@@ -11,7 +11,7 @@
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
-#define EIG_THREADS 1024
+#define EIG_THREADS 512
 #define EIG_CL 8
 
 __device__ __forceinline__ double warp_sum(double v) {

@@ -322,12 +322,18 @@ static int fold_impl(dmp2_engine* e, const uint8_t* msa, int N, int L, const flo
     int evi = 0;
     auto mark = [&]() { if (timed) cudaEventRecord(e->ev[evi++], st); };
     mark();
-    TRY(run_reweight(e, msa, N, L, ws.seqw, st));
-    TRY(run_dca(e, msa, N, L, ws.seqw, ws.feat, st));
-    mark();
+    // The MSA features (reweight + DCA) and the 1-D track (vgru + hgru) are independent until the stem: the
+    // features run on the engine's side stream, forked from and joined back into the caller's stream.
+    CUDA_TRY(e, cudaEventRecord(e->ev_fork, st));
+    CUDA_TRY(e, cudaStreamWaitEvent(e->side, e->ev_fork, 0));
+    TRY(run_reweight(e, msa, N, L, ws.seqw, e->side));
+    TRY(run_dca(e, msa, N, L, ws.seqw, ws.feat, e->side));
+    CUDA_TRY(e, cudaEventRecord(e->ev_join, e->side));
     TRY(run_vgru(e, msa, N, L, ws.v_last, st));
     mark();
     TRY(run_bigru(e, e->w.hgru, 2, ws.v_last, L, ws.mat1d_t, st));
+    mark();
+    CUDA_TRY(e, cudaStreamWaitEvent(st, e->ev_join, 0));
     mark();
     TRY(run_stem_base(e, ws.mat1d_t, ws.feat, L, st));
     if (tmpl) TRY(run_dmap(e, tmpl, L, ws.dmap, false, st));          // predict.py:142-143
@@ -384,6 +390,9 @@ int dmp2_create(dmp2_engine** out, int device, int n_tensors, const char* const*
         return s;
     }
     for (int i = 0; i < 16; i++) cudaEventCreate(&e->ev[i]);
+    cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming);
     e->ev_ok = true;
     const char* mode = getenv("DMP2_CONV_MODE");
     if (mode) {
@@ -409,6 +418,9 @@ void dmp2_destroy(dmp2_engine* e) {
     free_workspace(e);
     for (void* p : e->weight_allocs) cudaFree(p);
     if (e->ev_ok) for (int i = 0; i < 16; i++) cudaEventDestroy(e->ev[i]);
+    if (e->side) cudaStreamDestroy(e->side);
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    if (e->ev_join) cudaEventDestroy(e->ev_join);
     for (auto& ev : e->prof_ev) cudaEventDestroy(ev);
     delete e;
 }

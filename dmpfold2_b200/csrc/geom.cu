@@ -2,6 +2,8 @@
 // (network.py:106-137), the backbone build (network.py:141-177) and the on-device best-of-n selection
 // (network.py:302-306).
 #include "common.cuh"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 __global__ void k_fill(float* __restrict__ p, int64_t n, float v) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -30,26 +32,33 @@ int run_dmap(dmp2_engine* e, const float* ca, int L, float* dmap, bool clamp, cu
 }
 
 // ---------------------------------------------------------------------------------------------------
-// refine_coords: one persistent CTA, coordinates double-buffered in shared memory, S threads per atom (each
-// scans a strided share of the partners).  No L x L x 3 tensors, no autograd.  Pairs at >= 3.0 A contribute
-// exactly zero force in the reference (violate = 0), so they are skipped on the squared distance.
+// refine_coords: one 8-CTA cluster, every CTA keeps the full trace double-buffered in shared memory and
+// integrates a contiguous eighth of the atoms with S threads per atom; the new positions are broadcast to
+// the peers through distributed shared memory, one cluster barrier per step.  No L x L x 3 tensors, no
+// autograd.  Pairs at >= 3.0 A contribute exactly zero force in the reference (violate = 0), so they are
+// skipped on the squared distance.
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024, 1) k_refine(float* __restrict__ ca, int L, int steps, int S, int Lp) {
+#define REFINE_CL 8
+__global__ void __cluster_dims__(REFINE_CL, 1, 1) __launch_bounds__(1024, 1)
+k_refine(float* __restrict__ ca, int L, int steps, int per, int S) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int c = (int)cluster.block_rank();
     extern __shared__ float sh[];
     float* buf[2] = {sh, sh + 3 * L};
-    float* part = sh + 6 * L;                         // [S][3][Lp] partial accelerations
-    for (int i = threadIdx.x; i < 3 * L; i += blockDim.x) sh[i] = ca[i];
-    __syncthreads();
-    const int j = threadIdx.x % Lp, sub = threadIdx.x / Lp;
-    const bool act = j < L && sub < S;
+    float* part = sh + 6 * L;                         // [per][S][3] partial accelerations
+    for (int i = threadIdx.x; i < 3 * L; i += blockDim.x) { sh[i] = ca[i]; sh[3 * L + i] = ca[i]; }
+    cluster.sync();
+    const int jl = threadIdx.x / S, sub = threadIdx.x - jl * S;
+    const int j = c * per + jl;
+    const bool act = jl < per && j < L;
     for (int s = 0; s < steps; s++) {
-        const float* c = buf[s & 1];
+        const float* cc = buf[s & 1];
         float* o = buf[(s & 1) ^ 1];
         float ax = 0.f, ay = 0.f, az = 0.f, cx = 0.f, cy = 0.f, cz = 0.f;
         if (act) {
-            cx = c[3 * j]; cy = c[3 * j + 1]; cz = c[3 * j + 2];
+            cx = cc[3 * j]; cy = cc[3 * j + 1]; cz = cc[3 * j + 2];
             for (int i = sub; i < L; i += S) {
-                float dx = cx - c[3 * i], dy = cy - c[3 * i + 1], dz = cz - c[3 * i + 2];
+                float dx = cx - cc[3 * i], dy = cy - cc[3 * i + 1], dz = cz - cc[3 * i + 2];
                 float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
                 if (d2 < 9.0f) {
                     float d = fmaxf(sqrtf(d2), 0.01f);
@@ -57,73 +66,40 @@ __global__ void __launch_bounds__(1024, 1) k_refine(float* __restrict__ ca, int 
                     ax += f * (dx / d); ay += f * (dy / d); az += f * (dz / d);
                 }
             }
-            if (S > 1) { part[(sub * 3 + 0) * Lp + j] = ax; part[(sub * 3 + 1) * Lp + j] = ay; part[(sub * 3 + 2) * Lp + j] = az; }
+            float* pp = part + (jl * S + sub) * 3;
+            pp[0] = ax; pp[1] = ay; pp[2] = az;
         }
-        if (S > 1) __syncthreads();
+        __syncthreads();
         if (act && sub == 0) {
-            for (int q = 1; q < S; q++) { ax += part[(q * 3 + 0) * Lp + j]; ay += part[(q * 3 + 1) * Lp + j]; az += part[(q * 3 + 2) * Lp + j]; }
+            ax = 0.f; ay = 0.f; az = 0.f;
+            for (int q = 0; q < S; q++) { const float* pp = part + (jl * S + q) * 3; ax += pp[0]; ay += pp[1]; az += pp[2]; }
             if (j < L - 1) {              // bond to j+1: accels[j] += acov_j
-                float ux = c[3 * j + 3] - cx, uy = c[3 * j + 4] - cy, uz = c[3 * j + 5] - cz;
+                float ux = cc[3 * j + 3] - cx, uy = cc[3 * j + 4] - cy, uz = cc[3 * j + 5] - cz;
                 float d = fmaxf(sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(ux, ux), __fmul_rn(uy, uy)), __fmul_rn(uz, uz))), 0.1f);
                 float f = 100.0f * fminf(d - 3.78f, 3.0f);
                 ax += f * (ux / d); ay += f * (uy / d); az += f * (uz / d);
             }
             if (j > 0) {                  // bond from j-1: accels[j] -= acov_{j-1}
-                float ux = cx - c[3 * j - 3], uy = cy - c[3 * j - 2], uz = cz - c[3 * j - 1];
+                float ux = cx - cc[3 * j - 3], uy = cy - cc[3 * j - 2], uz = cz - cc[3 * j - 1];
                 float d = fmaxf(sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(ux, ux), __fmul_rn(uy, uy)), __fmul_rn(uz, uz))), 0.1f);
                 float f = 100.0f * fminf(d - 3.78f, 3.0f);
                 ax -= f * (ux / d); ay -= f * (uy / d); az -= f * (uz / d);
             }
-            o[3 * j] = cx + fminf(fmaxf(ax, -100.f), 100.f) * 0.001f;
-            o[3 * j + 1] = cy + fminf(fmaxf(ay, -100.f), 100.f) * 0.001f;
-            o[3 * j + 2] = cz + fminf(fmaxf(az, -100.f), 100.f) * 0.001f;
+            const float nx = cx + fminf(fmaxf(ax, -100.f), 100.f) * 0.001f;
+            const float ny = cy + fminf(fmaxf(ay, -100.f), 100.f) * 0.001f;
+            const float nz = cz + fminf(fmaxf(az, -100.f), 100.f) * 0.001f;
+#pragma unroll
+            for (int d = 0; d < REFINE_CL; d++) {
+                float* r = cluster.map_shared_rank(o, d);
+                r[3 * j] = nx; r[3 * j + 1] = ny; r[3 * j + 2] = nz;
+            }
         }
-        __syncthreads();
+        cluster.sync();
     }
-    const float* c = buf[steps & 1];
-    for (int i = threadIdx.x; i < 3 * L; i += blockDim.x) ca[i] = c[i];
-}
-
-// L > 1024: several atoms per thread are not supported by the single-CTA layout above; use a simple multi-pass variant
-__global__ void __launch_bounds__(1024, 1) k_refine_large(float* __restrict__ ca, int L, int steps) {
-    extern __shared__ float sh[];
-    float* buf[2] = {sh, sh + 3 * L};
-    for (int i = threadIdx.x; i < 3 * L; i += blockDim.x) sh[i] = ca[i];
-    __syncthreads();
-    for (int s = 0; s < steps; s++) {
-        const float* c = buf[s & 1];
-        float* o = buf[(s & 1) ^ 1];
-        for (int j = threadIdx.x; j < L; j += blockDim.x) {
-            float cx = c[3 * j], cy = c[3 * j + 1], cz = c[3 * j + 2], ax = 0.f, ay = 0.f, az = 0.f;
-            for (int i = 0; i < L; i++) {
-                float dx = cx - c[3 * i], dy = cy - c[3 * i + 1], dz = cz - c[3 * i + 2];
-                float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-                if (d2 < 9.0f) {
-                    float d = fmaxf(sqrtf(d2), 0.01f);
-                    float f = 100.0f * (3.0f - d);
-                    ax += f * (dx / d); ay += f * (dy / d); az += f * (dz / d);
-                }
-            }
-            if (j < L - 1) {
-                float ux = c[3 * j + 3] - cx, uy = c[3 * j + 4] - cy, uz = c[3 * j + 5] - cz;
-                float d = fmaxf(sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(ux, ux), __fmul_rn(uy, uy)), __fmul_rn(uz, uz))), 0.1f);
-                float f = 100.0f * fminf(d - 3.78f, 3.0f);
-                ax += f * (ux / d); ay += f * (uy / d); az += f * (uz / d);
-            }
-            if (j > 0) {
-                float ux = cx - c[3 * j - 3], uy = cy - c[3 * j - 2], uz = cz - c[3 * j - 1];
-                float d = fmaxf(sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(ux, ux), __fmul_rn(uy, uy)), __fmul_rn(uz, uz))), 0.1f);
-                float f = 100.0f * fminf(d - 3.78f, 3.0f);
-                ax -= f * (ux / d); ay -= f * (uy / d); az -= f * (uz / d);
-            }
-            o[3 * j] = cx + fminf(fmaxf(ax, -100.f), 100.f) * 0.001f;
-            o[3 * j + 1] = cy + fminf(fmaxf(ay, -100.f), 100.f) * 0.001f;
-            o[3 * j + 2] = cz + fminf(fmaxf(az, -100.f), 100.f) * 0.001f;
-        }
-        __syncthreads();
+    if (c == 0) {
+        const float* cc = buf[steps & 1];
+        for (int i = threadIdx.x; i < 3 * L; i += blockDim.x) ca[i] = cc[i];
     }
-    const float* c = buf[steps & 1];
-    for (int i = threadIdx.x; i < 3 * L; i += blockDim.x) ca[i] = c[i];
 }
 
 int run_refine(dmp2_engine* e, float* ca, int L, int steps, cudaStream_t st) {
@@ -131,20 +107,14 @@ int run_refine(dmp2_engine* e, float* ca, int L, int steps, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
         CUDA_TRY(e, cudaFuncSetAttribute(k_refine, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        CUDA_TRY(e, cudaFuncSetAttribute(k_refine_large, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
     }
-    if (L > 1024) {
-        size_t smem = (size_t)6 * L * sizeof(float);
-        if (smem > 200 * 1024) return e->fail(DMP2_ERR_UNSUPPORTED, "refine: L too large");
-        k_refine_large<<<1, 1024, smem, st>>>(ca, L, steps);
-        POST_LAUNCH(e, "k_refine_large");
-        return 0;
-    }
-    const int Lp = (L + 31) & ~31;
-    const int S = 1024 / Lp;                          // threads per atom
-    size_t smem = ((size_t)6 * L + (size_t)S * 3 * Lp) * sizeof(float);
-    k_refine<<<1, 1024, smem, st>>>(ca, L, steps, S, Lp);
+    const int per = cdiv(L, REFINE_CL);
+    if (per > 1024) return e->fail(DMP2_ERR_UNSUPPORTED, "refine: L too large");
+    const int S = 1024 / per;                         // threads per atom
+    size_t smem = ((size_t)6 * L + (size_t)per * S * 3) * sizeof(float);
+    if (smem > 200 * 1024) return e->fail(DMP2_ERR_UNSUPPORTED, "refine: L too large");
+    k_refine<<<REFINE_CL, 1024, smem, st>>>(ca, L, steps, per, S);
     POST_LAUNCH(e, "k_refine");
     return 0;
 }

@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, 'libdmp2.so')
 
 CONV_TC_F16X3, CONV_TC_F16, CONV_FFMA, CONV_TC_F16F8 = 0, 1, 2, 3
 CONV_MODES = {'f16x3': CONV_TC_F16X3, 'f16': CONV_TC_F16, 'ffma': CONV_FFMA, 'f16f8': CONV_TC_F16F8}
-STAGE_NAMES = ('msa_features', 'vgru', 'hgru', 'stem_base', 'recycling_passes', 'final_refine_backbone')
+STAGE_NAMES = ('vgru', 'hgru', 'msa_features_exposed', 'stem_base', 'recycling_passes', 'final_refine_backbone')
 
 _lib = None
 

@@ -62,7 +62,8 @@ int dmp2_set_conv_mode(dmp2_engine* e, int mode /* dmp2_conv_mode */);
 /* Number of this library's kernels launched by the engine since creation (bench.py's gpu_launches). */
 int64_t dmp2_launch_count(const dmp2_engine* e);
 /* Per-stage device time of the last dmp2_fold_host call, in ms (CUDA events): out[0..n) in the order
- * features, vgru, hgru, stem, resnet(conv+norm), head+eig, coord_gru, refine+backbone.  Returns n. */
+ * vgru, hgru, MSA features not hidden behind the vgru (they run on a side stream), stem base, all recycling
+ * passes, final refine + backbone.  Returns n (6). */
 int dmp2_stage_times(const dmp2_engine* e, float* out_ms, int cap);
 
 /* Debug: device time (us) of the four phases of the last top-8 eigensolve at size L (tridiagonalisation,

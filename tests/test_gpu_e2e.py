@@ -98,3 +98,37 @@ def test_python_api_and_cli(pf10963, tmp_path):
     assert len(out) == 2 + 82 * 5 - n_gly
     with pytest.raises(RuntimeError):
         aln_to_coords(aln, template=os.path.join(GOLDEN, 'PF10963.aln'))   # no CA atoms -> size mismatch
+
+
+def test_cfg3_shape_vs_oracle(eng, oracle, pf10963):
+    """BASELINE.json configs[2] shape (L=150, N=512), 2 recycles + 20 minimiser steps, against the oracle."""
+    msa = O.synth_msa_structured(pf10963, 150, 512, 7)
+    ref_c, ref_f = oracle.fold(msa, iterations=2, minsteps=20)
+    eng.set_conv_mode('f16f8')
+    coords, conf = eng.fold_host(msa, None, 2, 20)
+    _check(coords, conf, {'coords': ref_c.numpy(), 'confs': ref_f.numpy()})
+
+
+def _geometry_ok(coords):
+    ca = coords[:, 1]
+    bonds = np.linalg.norm(ca[1:] - ca[:-1], axis=1)
+    n_ca = np.linalg.norm(coords[:, 0] - ca, axis=1)
+    assert np.isfinite(coords).all()
+    assert bonds.min() > 2.5 and bonds.max() < 5.2, (bonds.min(), bonds.max())     # bond springs pull towards 3.78 A
+    assert n_ca[1:].min() > 0.9 and n_ca[1:].max() < 2.1, (n_ca.min(), n_ca.max())
+
+
+def test_cfg4_long_target_properties(eng, pf10963):
+    """BASELINE.json configs[3] shape (L=1024, N=2048, template-seeded) at a bounded iteration count: the oracle
+    needs ~1 h of CPU for this size, so the check is on size-independent properties -- finite output, chain
+    geometry after the minimiser, bit-reproducibility, and that the template seed changes the result."""
+    msa = O.synth_msa_structured(pf10963, 1024, 2048, 11)
+    eng.set_conv_mode('f16f8')
+    c0, f0 = eng.fold_host(msa, None, 0, 200)
+    _geometry_ok(c0)
+    assert f0.min() >= 0.0 and f0.max() <= 1.0
+    c1, f1 = eng.fold_host(msa, c0[:, 1].copy(), 1, 200)              # template = own CA trace (SURVEY 8c)
+    _geometry_ok(c1)
+    c2, f2 = eng.fold_host(msa, c0[:, 1].copy(), 1, 200)
+    assert np.array_equal(c1, c2) and np.array_equal(f1, f2)
+    assert not np.array_equal(c1, c0)
