@@ -82,6 +82,32 @@ int run_vgru_ffma(dmp2_engine* e, const uint8_t* msa, int N, int L, float* out, 
 // 96 x 256 slice of W_hh for its 32 hidden units in REGISTERS (64 per thread), reads h from shared
 // memory and broadcasts its 32 new values to the 7 peers through distributed shared memory each step.
 // ---------------------------------------------------------------------------------------------------
+// Per step the 32 new hidden values of a CTA travel to every peer as st.async stores that complete_tx on the
+// destination CTA's mbarrier: data and "ready" signal in one DSMEM operation, no cluster-wide barrier in the loop.
+__device__ __forceinline__ uint32_t gru_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t gru_mapa(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void gru_st_async(uint32_t dst, float v, uint32_t bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+                 ::"r"(dst), "r"(__float_as_uint(v)), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void gru_bar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    long long t0 = clock64();
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) break;
+        if (clock64() - t0 > 4000000000LL) { printf("k_bigru_rec: barrier timeout\n"); __trap(); }
+    }
+}
+
 __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(384, 1)
 k_bigru_rec(const float* __restrict__ gi, const float* __restrict__ whh_f, const float* __restrict__ bhh_f,
             const float* __restrict__ whh_b, const float* __restrict__ bhh_b, float* __restrict__ out, int L) {
@@ -92,6 +118,7 @@ k_bigru_rec(const float* __restrict__ gi, const float* __restrict__ whh_f, const
     const float* bhh = dir ? bhh_b : bhh_f;
     __shared__ __align__(16) float hbuf[2][256];
     __shared__ float part[4][96];
+    __shared__ __align__(8) unsigned long long hbar[2];
     const int tid = threadIdx.x;
     const int r = tid % 96, q = tid / 96;
     const int g = r >> 5, jj = r & 31;
@@ -108,15 +135,34 @@ k_bigru_rec(const float* __restrict__ gi, const float* __restrict__ whh_f, const
     const int j = 32 * c + tid;                       // hidden unit of the gate threads (tid < 32)
     if (tid < 32) { b_r = bhh[j]; b_z = bhh[256 + j]; b_n = bhh[512 + j]; }
     for (int i = tid; i < 512; i += 384) (&hbuf[0][0])[i] = 0.f;
+    const uint32_t bar0 = gru_smem_u32(&hbar[0]);     // barrier b lives at bar0 + 8*b
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // peer addresses of my slot in the h buffers and of the peers' barriers
+    uint32_t peer_h[8], peer_bar[8];                 // buffer/barrier 0; buffer 1 is +1024 bytes, barrier 1 is +8 bytes
+    if (tid < 32) {
+#pragma unroll
+        for (int d = 0; d < 8; d++) {
+            peer_h[d] = gru_mapa(gru_smem_u32(&hbuf[0][j]), d);
+            peer_bar[d] = gru_mapa(bar0, d);
+        }
+    }
     cluster.sync();
+    uint32_t ph = 0;                                  // phase parity bits of the two barriers
     for (int t = 0; t < L; t++) {
         const int te = dir ? (L - 1 - t) : t;
-        const int cur = t & 1;
+        const int cur = t & 1, nxt = cur ^ 1;
         float gi_r = 0.f, gi_z = 0.f, gi_n = 0.f;
         if (tid < 32) {
             const float* gp = gi + (int64_t)te * 1536 + dir * 768 + j;
             gi_r = gp[0]; gi_z = gp[256]; gi_n = gp[512];
         }
+        if (tid == 0 && t + 1 < L)                    // arm the barrier that collects the 256 values of step t+1's input
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8 * nxt), "r"(1024u) : "memory");
+        if (t > 0) { gru_bar_wait(bar0 + 8 * cur, (ph >> cur) & 1u); ph ^= 1u << cur; }
         const float4* h4 = reinterpret_cast<const float4*>(&hbuf[cur][64 * q]);
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
@@ -138,14 +184,15 @@ k_bigru_rec(const float* __restrict__ gi, const float* __restrict__ whh_f, const
             float nn = tanhf(gi_n + rr * gh_n);
             float hn = (1.0f - zz) * nn + zz * hbuf[cur][j];
             out[(int64_t)te * 512 + dir * 256 + j] = hn;
+            if (t + 1 < L) {
 #pragma unroll
-            for (int d = 0; d < 8; d++) {
-                float* remote = cluster.map_shared_rank(&hbuf[cur ^ 1][0], d);
-                remote[j] = hn;
+                for (int d = 0; d < 8; d++) gru_st_async(peer_h[d] + nxt * 1024, hn, peer_bar[d] + nxt * 8);
             }
         }
-        cluster.sync();
+        // No second block barrier: `part` is rewritten only after the next step's mbarrier wait, which completes
+        // only once this CTA's own gate threads have issued their stores, i.e. finished reading `part`.
     }
+    cluster.sync();                                   // nobody exits while a peer could still be storing into it
 }
 
 template <class AL>
