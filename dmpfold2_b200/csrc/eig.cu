@@ -8,6 +8,7 @@
 //   3. inverse iteration + Gram-Schmidt, 4. back-transformation                      }
 //   5. canonical sign (largest-|component| positive, lowest index wins ties), sqrt(clamp(relu(l),1e-8)) scaling.
 #include "common.cuh"
+#include "cluster_comm.cuh"
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
@@ -110,39 +111,55 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
     cluster.sync();
 
     // ---------------- 1. Householder tridiagonalisation ----------------------------------------------------
-    // Per column: 2 cluster barriers (all-gather of the column, all-gather of A v) + 3 block barriers.  The first
-    // component of the Householder vector (v0) is carried in a register, so the gathered column is never patched.
+    // Per column two all-gathers across the cluster (the column itself, then A v).  Every value travels as an
+    // st.async store that complete_tx's on the destination CTA's mbarrier, so there is no cluster-wide barrier in
+    // the loop: a CTA waits only until its own copy of the gathered vector is complete.  Buffers and barriers are
+    // ping-ponged by column parity; a CTA can run at most one gather ahead of its slowest peer.
+    // The first component of the Householder vector (v0) is carried in a register, the gathered column is never
+    // patched.
     __shared__ double scr_a[EIG_THREADS / 32], scr_b[EIG_THREADS / 32];
+    __shared__ __align__(8) unsigned long long gbar[4];          // [column gather | p gather][parity]
+    const uint32_t gbar0 = cc::smem_u32(&gbar[0]);
+    if (tid == 0) {
+        for (int i = 0; i < 4; i++) cc::bar_init(gbar0 + 8 * i, 1);
+        cc::bar_init_fence();
+    }
+    const uint32_t sp_a = cc::smem_u32(spb);
+    uint32_t peer_sv[EIG_CL], peer_bar[EIG_CL];                   // peers' svb / gbar base addresses
+#pragma unroll
+    for (int d = 0; d < EIG_CL; d++) {
+        peer_sv[d] = cc::mapa(cc::smem_u32(svb), d);
+        peer_bar[d] = cc::mapa(gbar0, d);
+    }
+    cluster.sync();
+    uint32_t gph = 0;                                             // phase parity bits of the four barriers
     for (int k = 0; k < n - 2; k++) {
         const int m = n - k - 1;                       // length of the column below the diagonal
         const int pp = k & 1;
         double* sv = svb + pp * n;
         double* sp = spb + pp * n;
+        const uint32_t bar_col = gbar0 + 8 * pp, bar_p = gbar0 + 8 * (2 + pp);
         const int li0 = (k + 1 - c + EIG_CL - 1) / EIG_CL;           // first local row with global index > k
+        if (tid == 0) { cc::bar_expect_tx(bar_col, (uint32_t)m * 8u); cc::bar_expect_tx(bar_p, (uint32_t)m * 8u); }
         for (int li = li0 + tid; li < nloc; li += EIG_THREADS) {
             const int i = li * EIG_CL + c;
             const double x = rbase[li * rstride + k];
+            const uint32_t off = (uint32_t)(pp * n + i - k - 1) * 8u;
 #pragma unroll
-            for (int d = 0; d < EIG_CL; d++) cluster.map_shared_rank(sv, d)[i - k - 1] = x;
+            for (int d = 0; d < EIG_CL; d++) cc::st_async_f64(peer_sv[d] + off, x, peer_bar[d] + 8 * pp);
         }
         if (tid == 0 && (k % EIG_CL) == c) gd[k] = rbase[(k / EIG_CL) * rstride + k];
-        cluster.sync();
+        cc::bar_wait(bar_col, (gph >> pp) & 1u);
+        gph ^= 1u << pp;
         double part = 0.0;
         for (int i = tid; i < m; i += EIG_THREADS) part += sv[i] * sv[i];
         const double sigma = block_sum1(part, scr_a);
         const double x0 = sv[0];
         const double tail = sigma - x0 * x0;
-        if (!(tail > 0.0)) {                           // column already tridiagonal: no reflector
-            if (c == 0) {
-                if (tid == 0) { ge[k] = x0; beta[k] = 0.0; }
-                for (int i = tid; i < m; i += EIG_THREADS) V[(int64_t)k * n + i] = 0.0;
-            }
-            cluster.sync();                            // keep the barrier count per column uniform
-            continue;
-        }
-        const double alpha = (x0 >= 0.0) ? -sqrt(sigma) : sqrt(sigma);
+        const bool reflect = tail > 0.0;               // false: column already tridiagonal, H = I
+        const double alpha = reflect ? ((x0 >= 0.0) ? -sqrt(sigma) : sqrt(sigma)) : x0;
         const double v0 = x0 - alpha;
-        const double bt = 2.0 / (tail + v0 * v0);
+        const double bt = reflect ? 2.0 / (tail + v0 * v0) : 0.0;
         if (c == 0) {
             if (tid == 0) { ge[k] = alpha; beta[k] = bt; }
             for (int i = tid; i < m; i += EIG_THREADS) V[(int64_t)k * n + i] = i == 0 ? v0 : sv[i];
@@ -156,22 +173,27 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
             for (; j + 32 < m; j += 64) { acc += row[j] * sv[j]; acc2 += row[j + 32] * sv[j + 32]; }
             if (j < m) acc += row[j] * sv[j];
             acc = warp_sum(acc + acc2) * bt;
-            if (lane < EIG_CL) cluster.map_shared_rank(sp, lane)[li * EIG_CL + c - k - 1] = acc;
+            if (lane < EIG_CL)
+                cc::st_async_f64(cc::mapa(sp_a, lane) + (uint32_t)(pp * n + li * EIG_CL + c - k - 1) * 8u, acc,
+                                 cc::mapa(gbar0, lane) + 8 * (2 + pp));
         }
-        cluster.sync();
+        cc::bar_wait(bar_p, (gph >> (2 + pp)) & 1u);
+        gph ^= 1u << (2 + pp);
         double pv = 0.0;
         for (int i = tid; i < m; i += EIG_THREADS) pv += sp[i] * (i == 0 ? v0 : sv[i]);
         const double kk = 0.5 * bt * block_sum1(pv, scr_b);
-        // rank-2 update of the owned rows with w = p - kk v formed on the fly
-        for (int li = li0 + warp; li < nloc; li += NW) {
-            double* row = rbase + li * rstride + (k + 1);
-            const int i = li * EIG_CL + c - k - 1;
-            const double vi = i == 0 ? v0 : sv[i];
-            const double wi = sp[i] - kk * vi;
+        // rank-2 update of the owned rows with w = p - kk v formed on the fly (bt == 0 -> p == 0 -> no change)
+        if (reflect) {
+            for (int li = li0 + warp; li < nloc; li += NW) {
+                double* row = rbase + li * rstride + (k + 1);
+                const int i = li * EIG_CL + c - k - 1;
+                const double vi = i == 0 ? v0 : sv[i];
+                const double wi = sp[i] - kk * vi;
 #pragma unroll 4
-            for (int j = lane; j < m; j += 32) {
-                const double vj = j == 0 ? v0 : sv[j];
-                row[j] -= vi * (sp[j] - kk * vj) + wi * vj;
+                for (int j = lane; j < m; j += 32) {
+                    const double vj = j == 0 ? v0 : sv[j];
+                    row[j] -= vi * (sp[j] - kk * vj) + wi * vj;
+                }
             }
         }
         __syncthreads();

@@ -60,6 +60,10 @@ __device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + ex
 __global__ void __launch_bounds__(VT_THREADS, 1) k_vgru_step(const __grid_constant__ VtMaps maps, const VtParams p) {
     const int role_id = blockIdx.z;
     const VtRole& R = p.role[role_id];
+    // Programmatic dependent launch: let the next step's grid be scheduled as soon as SMs free up; its prologue
+    // (barrier init, TMEM allocation) then overlaps our tail.  Nothing below touches global memory before
+    // griddepcontrol.wait, which returns only when the previous step has completed and its writes are visible.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (!R.active) return;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -88,6 +92,7 @@ __global__ void __launch_bounds__(VT_THREADS, 1) k_vgru_step(const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     if (warp == 0) {
         if (lane == 0) {
@@ -261,7 +266,17 @@ int run_vgru_tc(dmp2_engine* e, const uint8_t* msa, int N, int L, float* out, cu
         const int t2 = s - 2;
         p.role[2] = {s >= 2, 2 + (t2 & 1), w.vt_bias[2], gi1[(s - 1) & 1], hf[2 + (t2 & 1)], hf[2 + ((t2 + 1) & 1)],
                      hi(2 + ((t2 + 1) & 1)), lo(2 + ((t2 + 1) & 1))};
-        k_vgru_step<<<grid, VT_THREADS, VT_SMEM, st>>>(S->maps, p);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(VT_THREADS);
+        cfg.dynamicSmemBytes = VT_SMEM;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        CUDA_TRY(e, cudaLaunchKernelEx(&cfg, k_vgru_step, S->maps, p));
         POST_LAUNCH(e, "k_vgru_step");
     }
     CUDA_TRY(e, cudaMemcpyAsync(out, hf[2 + (N & 1)], hsz * sizeof(float), cudaMemcpyDeviceToDevice, st));
