@@ -34,24 +34,31 @@ __device__ double block_sum(double v, double* red) {
     return red[32];
 }
 
-// Number of eigenvalues of the tridiagonal (d, e2 = e^2) that are < x: sign changes of the leading principal
-// minors p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2} (division-free Sturm sequence, rescaled against overflow;
-// a zero minor takes the sign opposite to its predecessor).  One FMA on the dependent chain per row.
+// Number of eigenvalues of the tridiagonal (d, e2 = e^2) that are < x = sign changes in the sequence of leading
+// principal minors p_-1 = 1, p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2} (division-free Sturm sequence).  One DFMA on
+// the dependent chain per row; signs are read from the high word with integer ops; a zero minor takes the sign
+// opposite to its predecessor; both running minors are rescaled by a power of two every 8 rows.
 __device__ __forceinline__ int sturm_count(const double* d, const double* e2, int n, double x) {
-    const double BIG = 1.3407807929942597e154, SMALL = 7.458340731200207e-155;   // 2^512, 2^-512
     double pm = 1.0, p = d[0] - x;
-    int cnt = p < 0.0;
-    if (p == 0.0) { p = -1e-300; cnt = 1; }
+    if (p == 0.0) p = -1e-300;
+    int sp = (unsigned)__double2hiint(p) >> 31;
+    int cnt = sp;
+    int i = 1;
+    while (i < n) {
+        const int iend = min(n, i + 8);
 #pragma unroll 8
-    for (int i = 1; i < n; i++) {
-        double t = e2[i - 1] * pm;
-        double pn = fma(d[i] - x, p, -t);
-        if (pn == 0.0) pn = p > 0.0 ? -1e-300 * fabs(p) - 1e-300 : 1e-300 * fabs(p) + 1e-300;
-        cnt += (pn < 0.0) != (p < 0.0);
-        pm = p; p = pn;
-        double ap = fabs(p);
-        if (ap > BIG) { p *= SMALL; pm *= SMALL; }
-        else if (ap < SMALL) { p *= BIG; pm *= BIG; }
+        for (; i < iend; i++) {
+            double pn = fma(d[i] - x, p, -(e2[i - 1] * pm));
+            const int hi = __double2hiint(pn), lo = __double2loint(pn);
+            if (((hi << 1) | lo) == 0) pn = sp ? 1e-300 : -1e-300;       // exact zero: opposite sign of its predecessor
+            const int sn = (unsigned)__double2hiint(pn) >> 31;
+            cnt += sn ^ sp;
+            sp = sn;
+            pm = p; p = pn;
+        }
+        const int ex = (__double2hiint(p) >> 20) & 0x7ff;
+        if (ex > 1023 + 400) { p *= 3.8725919148493183e-121; pm *= 3.8725919148493183e-121; }        // 2^-400
+        else if (ex < 1023 - 400) { p *= 2.5822498780869086e120; pm *= 2.5822498780869086e120; }      // 2^400
     }
     return cnt;
 }

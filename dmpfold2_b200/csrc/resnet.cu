@@ -200,7 +200,7 @@ int run_norm_gate(dmp2_engine* e, int blk, const float* raw, float* x, int L, bo
     const int64_t npix = (int64_t)L * L;
     const float* gamma = stem ? e->w.stem_gamma : e->w.blk[blk].gamma;
     const float* beta = stem ? e->w.stem_beta : e->w.blk[blk].beta;
-    int sgrid = (int)std::min<int64_t>(cdiv64(npix, 64), (int64_t)e->num_sms * 2);
+    int sgrid = (int)std::min<int64_t>(cdiv64(npix, 64), (int64_t)e->num_sms);     // few partials: the last CTA folds them serially
     k_in_stats<<<sgrid, 512, 0, st>>>(raw, npix, gamma, ws.stat_part, ws.ticket, ws.norm_ss);
     POST_LAUNCH(e, "k_in_stats");
     int agrid = (int)std::min<int64_t>(cdiv64(npix, 8), (int64_t)e->num_sms * 8);
