@@ -143,6 +143,8 @@ def main():
         run_reference(args, rank)
         return
 
+    if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
+        os.environ['NCCL_DEBUG'] = 'WARN'              # keep stdout to the one JSON line
     import torch
     import torch.distributed as dist
     from dmpfold2_b200.engine import Engine

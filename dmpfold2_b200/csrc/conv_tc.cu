@@ -268,6 +268,185 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv5_tc(const __grid_consta
     }
 }
 
+// ---- CTA-pair variant (cta_group::2) ---------------------------------------------------------------------
+// The two CTAs of a cluster own two adjacent 128-pixel tiles and behave as one 256 x 512 tile: every MMA is
+// M=256 N=256, issued by the leader CTA, reading the A rows of both CTAs and HALF of the B piece from each CTA's
+// shared memory.  Per CTA the weight stream through shared memory is halved (16 KB per piece instead of 32 KB),
+// which both halves the SM ingest bandwidth and doubles the number of B slots (pipeline depth) in the same 160 KB.
+constexpr int B2_BYTES = 128 * 128;       // per-CTA half of a B piece: 128 couts x 128 bytes
+constexpr int NUM_B2_SLOTS = 10;
+
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+k_conv5_tc2(const __grid_constant__ ConvMaps maps, const TcParams p) {
+    using C = Cfg<MODE>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t a_base = base;
+    const uint32_t b_base = base + C::NUM_A_STAGES * C::A_STAGE_BYTES;
+    const uint32_t bar_base = b_base + NUM_B2_SLOTS * B2_BYTES;
+    auto a_full = [&](int s) { return bar_base + 8u * s; };
+    auto a_empty = [&](int s) { return bar_base + 8u * (C::NUM_A_STAGES + s); };
+    auto b_full = [&](int s) { return bar_base + 8u * (2 * C::NUM_A_STAGES + s); };
+    auto b_empty = [&](int s) { return bar_base + 8u * (2 * C::NUM_A_STAGES + NUM_B2_SLOTS + s); };
+    const uint32_t acc_full = bar_base + 8u * (2 * C::NUM_A_STAGES + 2 * NUM_B2_SLOTS);
+    const uint32_t tmem_slot = acc_full + 8;
+    uint8_t* smem_gen = smem_raw + (base - smem_u32(smem_raw));
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - base));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = cluster_ctarank();
+    const bool leader = crank == 0;
+
+    const int y0 = (blockIdx.x / p.tiles_x) * TILE_H, x0 = (blockIdx.x % p.tiles_x) * TILE_W;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < C::NUM_A_STAGES; s++) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
+        for (int s = 0; s < NUM_B2_SLOTS; s++) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+        mbar_init(acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {                                 // both CTAs, same logical warp, same destination offset
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_gen;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs; full barriers live in the leader) =====================
+        if (lane == 0) {
+            int sa = 0, pa = 0, sb = 0, pb = 0;
+            for (int kb = 0; kb < p.num_kb; kb++) {
+                const int tap = kb >> 1, sub = kb & 1;
+                const int dy = tap / 5, dx = tap - dy * 5;
+                const int c1 = x0 + dx - 2, c2 = y0 + dy - 2;
+                mbar_wait(a_empty(sa), pa ^ 1);
+                const uint32_t afl = mapa_u32(a_full(sa), 0);
+                if (leader) mbar_expect_tx(a_full(sa), 2 * C::A_STAGE_BYTES);
+                const uint32_t ast = a_base + sa * C::A_STAGE_BYTES;
+                if (MODE == M_F16) {
+                    tma2_load_3d(ast, &maps.a_hi, afl, sub * KCHUNK, c1, c2);
+                } else if (MODE == M_F16X3) {
+                    tma2_load_3d(ast, &maps.a_hi, afl, sub * KCHUNK, c1, c2);
+                    tma2_load_3d(ast + A_BYTES, &maps.a_lo, afl, sub * KCHUNK, c1, c2);
+                } else if (sub == 0) {
+                    tma2_load_3d(ast, &maps.a_hi, afl, 0, c1, c2);
+                    tma2_load_3d(ast + A_BYTES, &maps.a_hi, afl, KCHUNK, c1, c2);
+                } else {
+                    tma2_load_3d(ast, &maps.a8_lo, afl, 0, c1, c2);
+                    tma2_load_3d(ast + A_BYTES, &maps.a8_hi, afl, 0, c1, c2);
+                }
+                if (++sa == C::NUM_A_STAGES) { sa = 0; pa ^= 1; }
+                for (int piece = 0; piece < C::PIECES; piece++) {
+                    const CUtensorMap* bm;
+                    int k0;
+                    if (MODE == M_F16F8) {
+                        if (sub == 0) { bm = &maps.b_hi; k0 = tap * 128 + (piece >> 1) * KCHUNK; }
+                        else { bm = (piece >> 1) ? &maps.b8_lo : &maps.b8_w; k0 = tap * 128; }
+                    } else {
+                        bm = piece < 2 ? &maps.b_hi : &maps.b_lo;
+                        k0 = kb * KCHUNK;
+                    }
+                    const int n0 = (piece & 1) * 256 + (int)crank * 128;      // my half of the 256 couts of this piece
+                    mbar_wait(b_empty(sb), pb ^ 1);
+                    const uint32_t bfl = mapa_u32(b_full(sb), 0);
+                    if (leader) mbar_expect_tx(b_full(sb), 2 * B2_BYTES);
+                    const uint32_t bdst = b_base + sb * B2_BYTES;
+                    tma2_load_2d(bdst, bm, bfl, k0, n0);
+                    tma2_load_2d(bdst + BQ_BYTES, bm, bfl, k0, n0 + BQ_ROWS);
+                    if (++sb == NUM_B2_SLOTS) { sb = 0; pb ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (lane == 0 && leader) {
+            const uint32_t idesc = make_idesc(256, 256);
+            const uint32_t idesc8 = make_idesc_f8(256, 256);
+            int sa = 0, pa = 0, sb = 0, pb = 0;
+            for (int kb = 0; kb < p.num_kb; kb++) {
+                const int sub = kb & 1;
+                mbar_wait(a_full(sa), pa);
+                const uint32_t a0 = a_base + sa * C::A_STAGE_BYTES;
+                const uint32_t a1 = a0 + A_BYTES;
+                for (int piece = 0; piece < C::PIECES; piece++) {
+                    mbar_wait(b_full(sb), pb);
+                    tc_fence_after();
+                    const uint32_t b_addr = b_base + sb * B2_BYTES;
+                    const uint32_t d = tmem_base + (uint32_t)(piece & 1) * 256u;
+                    if (MODE == M_F16F8) {
+                        const uint32_t a = (piece >> 1) ? a1 : a0;
+                        if (sub == 0) {
+                            const bool first = (kb == 0) && (piece < 2);
+#pragma unroll
+                            for (int k = 0; k < 4; k++)
+                                tc2_mma_f16(d, make_smem_desc(a + k * 32), make_smem_desc(b_addr + k * 32), idesc, !(first && k == 0));
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 4; k++)
+                                tc2_mma_f8(d, make_smem_desc(a + k * 32), make_smem_desc(b_addr + k * 32), idesc8, 1u);
+                        }
+                    } else {
+                        const bool first = (kb == 0) && (piece < 2);
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                            tc2_mma_f16(d, make_smem_desc(a0 + k * 32), make_smem_desc(b_addr + k * 32), idesc, !(first && k == 0));
+                        if (MODE == M_F16X3 && piece < 2) {
+#pragma unroll
+                            for (int k = 0; k < 4; k++)
+                                tc2_mma_f16(d, make_smem_desc(a1 + k * 32), make_smem_desc(b_addr + k * 32), idesc, 1u);
+                        }
+                    }
+                    tc2_commit_mc(b_empty(sb), 3);         // frees the slot in both CTAs
+                    if (++sb == NUM_B2_SLOTS) { sb = 0; pb ^= 1; }
+                }
+                tc2_commit_mc(a_empty(sa), 3);
+                if (++sa == C::NUM_A_STAGES) { sa = 0; pa ^= 1; }
+            }
+            tc2_commit_mc(acc_full, 3);
+        }
+    } else {
+        // ===================== epilogue (warps 2..5, each CTA drains its own 128 accumulator rows) =====================
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        const int y = y0 + (r >> 4), x = x0 + (r & 15);
+        const bool valid = (y < p.L) && (x < p.L);
+        const int64_t row = (int64_t)y * p.L + x;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        for (int ch = 0; ch < 16; ch++) {
+            uint32_t v[32];
+            tmem_ld32(lane_addr + ch * 32, v);
+            if (!valid) continue;
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + ch * 32 + 4 * i));
+                o[i] = fmaxf(fmaxf(__uint_as_float(v[4 * i]) + b.x, __uint_as_float(v[4 * i + 1]) + b.y),
+                             fmaxf(__uint_as_float(v[4 * i + 2]) + b.z, __uint_as_float(v[4 * i + 3]) + b.w));
+            }
+            float4* dst = reinterpret_cast<float4*>(p.out + row * 128 + ch * 8);
+            dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+            dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                              // the leader's MMAs read the peer's shared memory until the very end
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
 // ---- host side: tensor maps -----------------------------------------------------------------------------
 struct TcState {
     CUtensorMap wmap[DMP2_NBLOCKS][4];               // b_hi, b_lo, b8_w, b8_lo
@@ -294,6 +473,9 @@ int get_state(dmp2_engine* e, TcState** out) {
         TRY((set_attr<M_F16, 1>(e))); TRY((set_attr<M_F16, 2>(e))); TRY((set_attr<M_F16, 4>(e)));
         TRY((set_attr<M_F16X3, 1>(e))); TRY((set_attr<M_F16X3, 2>(e))); TRY((set_attr<M_F16X3, 4>(e)));
         TRY((set_attr<M_F16F8, 1>(e))); TRY((set_attr<M_F16F8, 2>(e))); TRY((set_attr<M_F16F8, 4>(e)));
+        CUDA_TRY(e, cudaFuncSetAttribute(k_conv5_tc2<M_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<M_F16>::SMEM_BYTES));
+        CUDA_TRY(e, cudaFuncSetAttribute(k_conv5_tc2<M_F16X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<M_F16X3>::SMEM_BYTES));
+        CUDA_TRY(e, cudaFuncSetAttribute(k_conv5_tc2<M_F16F8>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<M_F16F8>::SMEM_BYTES));
         s->attr_set = true;
     }
     *out = s;
@@ -333,7 +515,15 @@ int launch(dmp2_engine* e, const ConvMaps& maps, const TcParams& p, int grid, cu
 }
 
 template <int MODE>
+int launch_pair(dmp2_engine* e, const ConvMaps& maps, const TcParams& p, int grid, cudaStream_t st) {
+    k_conv5_tc2<MODE><<<(grid + 1) / 2 * 2, NUM_THREADS, Cfg<MODE>::SMEM_BYTES, st>>>(maps, p);
+    POST_LAUNCH(e, "k_conv5_tc2");
+    return 0;
+}
+
+template <int MODE>
 int launch_cl(dmp2_engine* e, int cl, const ConvMaps& maps, const TcParams& p, int grid, cudaStream_t st) {
+    if (cl == 0) return launch_pair<MODE>(e, maps, p, grid, st);
     if (cl == 4) return launch<MODE, 4>(e, maps, p, grid, st);
     if (cl == 2) return launch<MODE, 2>(e, maps, p, grid, st);
     return launch<MODE, 1>(e, maps, p, grid, st);

@@ -403,6 +403,7 @@ int dmp2_create(dmp2_engine** out, int device, int n_tensors, const char* const*
     }
     const char* cc = getenv("DMP2_CONV_CLUSTER");
     if (cc && (!strcmp(cc, "1") || !strcmp(cc, "2") || !strcmp(cc, "4"))) e->conv_cluster = atoi(cc);
+    if (cc && !strcmp(cc, "pair")) e->conv_cluster = 0;        // cta_group::2 CTA-pair kernel
     const char* vm = getenv("DMP2_VGRU");
     if (vm && !strcmp(vm, "ffma")) e->vgru_mode = 1;
     *out = e;

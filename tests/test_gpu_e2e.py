@@ -132,3 +132,15 @@ def test_cfg4_long_target_properties(eng, pf10963):
     c2, f2 = eng.fold_host(msa, c0[:, 1].copy(), 1, 200)
     assert np.array_equal(c1, c2) and np.array_equal(f1, f2)
     assert not np.array_equal(c1, c0)
+
+
+def test_cfg5_size_single_gpu_properties(eng, pf10963):
+    """BASELINE.json configs[4] image size (L=2048) on ONE GPU: with the 955/512-channel tensors never materialised
+    the whole target needs ~45 GB, so no halo split is required for capacity.  Bounded (N=1024, one pass);
+    size-independent properties only."""
+    msa = O.synth_msa_structured(pf10963, 2048, 1024, 13)
+    eng.set_conv_mode('f16f8')
+    c0, f0 = eng.fold_host(msa, None, 0, 100)
+    _geometry_ok(c0)
+    assert c0.shape == (2048, 5, 3) and f0.shape == (2048,)
+    assert f0.min() >= 0.0 and f0.max() <= 1.0

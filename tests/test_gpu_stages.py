@@ -219,3 +219,23 @@ def test_vgru_long_wavefront(eng, oracle, pf10963):
     assert (got - ref).abs().max() < 1e-4
     one = eng.vgru(msa[:1]).cpu()                      # N = 1: shortest wavefront
     assert (one - oracle.vgru_last(torch.from_numpy(msa[:1]))).abs().max() < 1e-5
+
+
+@pytest.mark.parametrize('cluster', ['pair', '1', '4'])
+def test_conv_cluster_variants(state_dict, oracle, cluster, monkeypatch):
+    """The conv kernel variants that share the weight stream differently (cta_group::2 CTA pairs, no cluster,
+    4-CTA multicast) must agree with the oracle exactly like the default (2-CTA multicast)."""
+    from dmpfold2_b200.engine import Engine
+    monkeypatch.setenv('DMP2_CONV_CLUSTER', cluster)
+    e = Engine(state_dict, 0)
+    try:
+        g = torch.Generator().manual_seed(77)
+        for l in (19, 82):                                   # odd tile counts exercise the padded dummy tiles
+            x = torch.randn(1, 128, l, l, generator=g) * 3
+            ref = _nhwc(_conv_ref(oracle, 5, x))
+            for mode, tol in (('f16x3', 2e-5), ('f16f8', 3e-4), ('f16', 3e-3)):
+                e.set_conv_mode(mode)
+                got = e.conv5_maxout(5, _nhwc(x)).cpu()
+                assert _rel(got, ref) < tol, (cluster, mode, l, _rel(got, ref))
+    finally:
+        e.close()
