@@ -229,6 +229,34 @@ def main():
         fast_ms = f0.elapsed_time(f1)
         eng.set_conv_mode(args.conv_mode)
 
+    # ---- informational: two engines on two streams of the same GPU folding alternate targets (the one-target-
+    # per-stream layout of BASELINE.json configs[2]): latency-bound stages of one target overlap the convs of the other
+    tp2_ms = None
+    try:
+        eng_b = Engine(sd, local_rank, conv_mode=args.conv_mode)
+        engines = (eng, eng_b)
+        streams = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+        def fold_pair_loop(idxs):
+            for k, i in enumerate(idxs):
+                with torch.cuda.stream(streams[k & 1]):
+                    engines[k & 1].fold(msas_dev[i], None, N_ITER, N_MIN)
+        fold_pair_loop(range(min(2, nsteps)))
+        torch.cuda.synchronize()
+        n_tp = max(2, (args.steps // 2) * 2)
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0e.record()
+        for s_ in streams:
+            s_.wait_stream(torch.cuda.current_stream(dev))
+        fold_pair_loop([args.warmup + (k % args.steps) for k in range(n_tp)])
+        for s_ in streams:
+            torch.cuda.current_stream(dev).wait_stream(s_)
+        t1e.record()
+        torch.cuda.synchronize()
+        tp2_ms = t0e.elapsed_time(t1e) / n_tp
+        eng_b.close()
+    except Exception as ex:                      # informational only
+        tp2_ms = f'failed: {ex}'
+
     if rank == 0:
         peaks = {}
         pk = os.path.join(ROOT, 'MEASURED_PEAKS.json')
@@ -263,6 +291,7 @@ def main():
                                  'f16f8 one fp16 MMA + two fp8 MMAs (2 fp16-equivalents)'},
             'stage_ms_last_e2e_step': stages,
             'fast_mode_f16_ms_per_target': fast_ms,
+            'two_streams_ms_per_target': tp2_ms,
         }
         if world == 1 and not args.no_cpu_baseline:
             v, desc = cpu_sample(sd, msas[-1])

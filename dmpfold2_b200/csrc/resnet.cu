@@ -126,7 +126,8 @@ __global__ void __launch_bounds__(256) k_norm_gate(const float* __restrict__ raw
                                                    const float* __restrict__ beta, const float* __restrict__ gate_c,
                                                    const float* __restrict__ sse_w, float sse_b, int stem, int64_t npix,
                                                    float* __restrict__ x, __half* __restrict__ xh, __half* __restrict__ xl,
-                                                   uint8_t* __restrict__ x8lo, uint8_t* __restrict__ x8hi) {
+                                                   uint8_t* __restrict__ x8lo, uint8_t* __restrict__ x8hi, int write_lo16,
+                                                   int write_fp8) {
     const int lane = threadIdx.x & 31;
     const int c = lane * 4;
     const float4 mean = *reinterpret_cast<const float4*>(norm + c);
@@ -160,10 +161,12 @@ __global__ void __launch_bounds__(256) k_norm_gate(const float* __restrict__ raw
         hv.x = *reinterpret_cast<uint32_t*>(&h01); hv.y = *reinterpret_cast<uint32_t*>(&h23);
         lv.x = *reinterpret_cast<uint32_t*>(&l01); lv.y = *reinterpret_cast<uint32_t*>(&l23);
         *reinterpret_cast<uint2*>(xh + p * 128 + c) = hv;
-        *reinterpret_cast<uint2*>(xl + p * 128 + c) = lv;
-        *reinterpret_cast<uint32_t*>(x8lo + p * 128 + c) =
-            pack_e4m3x4((o.x - f01.x) * 256.f, (o.y - f01.y) * 256.f, (o.z - f23.x) * 256.f, (o.w - f23.y) * 256.f);
-        *reinterpret_cast<uint32_t*>(x8hi + p * 128 + c) = pack_e4m3x4(f01.x * 0.0625f, f01.y * 0.0625f, f23.x * 0.0625f, f23.y * 0.0625f);
+        if (write_lo16) *reinterpret_cast<uint2*>(xl + p * 128 + c) = lv;            // only the f16x3 conv reads it
+        if (write_fp8) {                                                              // only the f16f8 conv reads these
+            *reinterpret_cast<uint32_t*>(x8lo + p * 128 + c) =
+                pack_e4m3x4((o.x - f01.x) * 256.f, (o.y - f01.y) * 256.f, (o.z - f23.x) * 256.f, (o.w - f23.y) * 256.f);
+            *reinterpret_cast<uint32_t*>(x8hi + p * 128 + c) = pack_e4m3x4(f01.x * 0.0625f, f01.y * 0.0625f, f23.x * 0.0625f, f23.y * 0.0625f);
+        }
     }
 }
 
@@ -206,7 +209,8 @@ int run_norm_gate(dmp2_engine* e, int blk, const float* raw, float* x, int L, bo
     int agrid = (int)std::min<int64_t>(cdiv64(npix, 8), (int64_t)e->num_sms * 8);
     k_norm_gate<<<agrid, 256, 0, st>>>(raw, ws.norm_ss, beta, stem ? nullptr : e->w.blk[blk].gate_c,
                                        stem ? nullptr : e->w.blk[blk].sse_w, stem ? 0.f : e->w.blk[blk].sse_b, stem ? 1 : 0,
-                                       npix, x, ws.xh, ws.xl, ws.x8lo, ws.x8hi);
+                                       npix, x, ws.xh, ws.xl, ws.x8lo, ws.x8hi, e->conv_mode == DMP2_CONV_TC_F16X3 ? 1 : 0,
+                                       e->conv_mode == DMP2_CONV_TC_F16F8 ? 1 : 0);
     POST_LAUNCH(e, "k_norm_gate");
     return 0;
 }

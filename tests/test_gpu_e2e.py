@@ -144,3 +144,13 @@ def test_cfg5_size_single_gpu_properties(eng, pf10963):
     _geometry_ok(c0)
     assert c0.shape == (2048, 5, 3) and f0.shape == (2048,)
     assert f0.min() >= 0.0 and f0.max() <= 1.0
+
+
+def test_cfg2_full_size_vs_oracle(eng, oracle, pf10963):
+    """The headline configuration itself (BASELINE.json configs[1]: L=300, N=1000, 10 iterations + 100 minimiser
+    steps) against the oracle (about half a minute of host CPU), default conv mode."""
+    msa = O.synth_msa_structured(pf10963, 300, 1000, 0)
+    ref_c, ref_f = oracle.fold(msa, iterations=10, minsteps=100)
+    eng.set_conv_mode('f16f8')
+    coords, conf = eng.fold_host(msa, None, 10, 100)
+    _check(coords, conf, {'coords': ref_c.numpy(), 'confs': ref_f.numpy()})
