@@ -427,11 +427,10 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
 }
 
 int run_eig_top8(dmp2_engine* e, const float* m, int L, float* vals, float* mds_scaled, float* vecs_raw, cudaStream_t st) {
-    static bool attr_set = false;
     constexpr size_t LIMIT = 200 * 1024;
-    if (!attr_set) {
+    if (!e->attr_eig) {
         CUDA_TRY(e, cudaFuncSetAttribute(k_eig_top8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LIMIT));
-        attr_set = true;
+        e->attr_eig = true;
     }
     const size_t n = (size_t)L;
     const size_t rows = ((n + EIG_CL - 1) / EIG_CL) * n;       // doubles per CTA

@@ -104,10 +104,9 @@ k_refine(float* __restrict__ ca, int L, int steps, int per, int S) {
 
 int run_refine(dmp2_engine* e, float* ca, int L, int steps, cudaStream_t st) {
     if (steps <= 0) return 0;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!e->attr_refine) {
         CUDA_TRY(e, cudaFuncSetAttribute(k_refine, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
+        e->attr_refine = true;
     }
     const int per = cdiv(L, REFINE_CL);
     if (per > 1024) return e->fail(DMP2_ERR_UNSUPPORTED, "refine: L too large");

@@ -65,12 +65,12 @@ __global__ void __launch_bounds__(512) k_in_stats(const float* __restrict__ raw,
     double s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
     const int64_t stride = (int64_t)gridDim.x * 16;
     int64_t p = (int64_t)blockIdx.x * 16 + grp;
-    for (; p + 3 * stride < npix; p += 4 * stride) {
-        float4 v[4];
+    for (; p + 7 * stride < npix; p += 8 * stride) {                // 8 independent 16-byte loads in flight per thread
+        float4 v[8];
 #pragma unroll
-        for (int u = 0; u < 4; u++) v[u] = *reinterpret_cast<const float4*>(raw + (p + u * stride) * 128 + lane * 4);
+        for (int u = 0; u < 8; u++) v[u] = *reinterpret_cast<const float4*>(raw + (p + u * stride) * 128 + lane * 4);
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < 8; u++) {
             s[0] += v[u].x; s[1] += v[u].y; s[2] += v[u].z; s[3] += v[u].w;
             ss[0] += (double)v[u].x * v[u].x; ss[1] += (double)v[u].y * v[u].y;
             ss[2] += (double)v[u].z * v[u].z; ss[3] += (double)v[u].w * v[u].w;
@@ -203,7 +203,7 @@ int run_norm_gate(dmp2_engine* e, int blk, const float* raw, float* x, int L, bo
     const int64_t npix = (int64_t)L * L;
     const float* gamma = stem ? e->w.stem_gamma : e->w.blk[blk].gamma;
     const float* beta = stem ? e->w.stem_beta : e->w.blk[blk].beta;
-    int sgrid = (int)std::min<int64_t>(cdiv64(npix, 64), (int64_t)e->num_sms);     // few partials: the last CTA folds them serially
+    int sgrid = (int)std::min<int64_t>(cdiv64(npix, 64), (int64_t)e->num_sms * 2);
     k_in_stats<<<sgrid, 512, 0, st>>>(raw, npix, gamma, ws.stat_part, ws.ticket, ws.norm_ss);
     POST_LAUNCH(e, "k_in_stats");
     int agrid = (int)std::min<int64_t>(cdiv64(npix, 8), (int64_t)e->num_sms * 8);
