@@ -178,6 +178,7 @@ struct dmp2_engine {
     void* vt_state = nullptr;        // tensor-core vgru state, owned by vgru_tc.cu
     int conv_cluster = 2;            // CTAs per cluster sharing the conv weight stream by TMA multicast (1 = off)
     int vgru_mode = 0;               // 0 = tensor cores (fp16x3), 1 = CUDA-core fp32 validation path
+    bool eig_no_cl16 = false;        // set when a 16-CTA cluster launch was refused
     bool attr_eig = false, attr_refine = false;   // per-engine (= per-device) cudaFuncSetAttribute done
     bool profile = false;            // record a CUDA-event pair around every conv launch (bench.py roofline)
     std::vector<cudaEvent_t> prof_ev;

@@ -13,7 +13,6 @@
 namespace cg = cooperative_groups;
 
 #define EIG_THREADS 512
-#define EIG_CL 8
 
 __device__ __forceinline__ double warp_sum(double v) {
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -77,7 +76,8 @@ __device__ __forceinline__ double block_sum1(double v, double* scr) {
 
 // rows_smem: doubles of shared memory reserved for the matrix rows (0 = rows stay in global memory A)
 // vec_smem:  1 = the inverse-iteration work vectors (32 n doubles) live in shared memory
-__global__ void __cluster_dims__(EIG_CL, 1, 1) __launch_bounds__(EIG_THREADS, 1)
+template <int EIG_CL>
+__global__ void __launch_bounds__(EIG_THREADS, 1)
 k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* __restrict__ V, double* __restrict__ wk,
            int rows_in_smem, int vec_in_smem, float* __restrict__ vals_out, float* __restrict__ mds_out,
            float* __restrict__ vec_out) {
@@ -176,7 +176,7 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
             const double* row = rbase + li * rstride + (k + 1);
             double acc = lane == 0 ? row[0] * v0 : 0.0, acc2 = 0.0;
             int j = lane == 0 ? 32 : lane;
-#pragma unroll 2
+#pragma unroll 4
             for (; j + 32 < m; j += 64) { acc += row[j] * sv[j]; acc2 += row[j + 32] * sv[j + 32]; }
             if (j < m) acc += row[j] * sv[j];
             acc = warp_sum(acc + acc2) * bt;
@@ -196,7 +196,7 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
                 const int i = li * EIG_CL + c - k - 1;
                 const double vi = i == 0 ? v0 : sv[i];
                 const double wi = sp[i] - kk * vi;
-#pragma unroll 4
+#pragma unroll 8
                 for (int j = lane; j < m; j += 32) {
                     const double vj = j == 0 ? v0 : sv[j];
                     row[j] -= vi * (sp[j] - kk * vj) + wi * vj;
@@ -426,25 +426,60 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
     stamp(4);
 }
 
+template <int CL>
+static int launch_eig(dmp2_engine* e, const float* m, int L, int rows_in_smem, int vec_in_smem, size_t smem, float* vals,
+                      float* mds_scaled, float* vecs_raw, cudaStream_t st) {
+    double* V = e->ws.eig_a + (int64_t)L * L;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CL);
+    cfg.blockDim = dim3(EIG_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CUDA_TRY(e, cudaLaunchKernelEx(&cfg, k_eig_top8<CL>, m, L, e->ws.eig_a, V, e->ws.eig_w, rows_in_smem, vec_in_smem, vals,
+                                   mds_scaled, vecs_raw));
+    POST_LAUNCH(e, "k_eig_top8");
+    return 0;
+}
+
 int run_eig_top8(dmp2_engine* e, const float* m, int L, float* vals, float* mds_scaled, float* vecs_raw, cudaStream_t st) {
-    constexpr size_t LIMIT = 200 * 1024;
+    constexpr size_t LIMIT = 216 * 1024;
     if (!e->attr_eig) {
-        CUDA_TRY(e, cudaFuncSetAttribute(k_eig_top8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LIMIT));
+        CUDA_TRY(e, cudaFuncSetAttribute(k_eig_top8<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LIMIT));
+        CUDA_TRY(e, cudaFuncSetAttribute(k_eig_top8<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LIMIT));
+        CUDA_TRY(e, cudaFuncSetAttribute(k_eig_top8<16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         e->attr_eig = true;
     }
     const size_t n = (size_t)L;
-    const size_t rows = ((n + EIG_CL - 1) / EIG_CL) * n;       // doubles per CTA
     const size_t vec = 32 * n;
-    int rows_in_smem = 0, vec_in_smem = 0;
-    size_t big = 0;
-    if ((7 * n + std::max(rows, vec)) * 8 <= LIMIT) { rows_in_smem = 1; vec_in_smem = 1; big = std::max(rows, vec); }
-    else if ((7 * n + rows) * 8 <= LIMIT) { rows_in_smem = 1; big = rows; }
-    else if ((7 * n + vec) * 8 <= LIMIT) { vec_in_smem = 1; big = vec; }
-    const size_t smem = (7 * n + big) * 8;
-    if (smem > LIMIT) return e->fail(DMP2_ERR_UNSUPPORTED, "eig_top8: L too large");
-    double* V = e->ws.eig_a + (int64_t)L * L;
-    k_eig_top8<<<EIG_CL, EIG_THREADS, smem, st>>>(m, L, e->ws.eig_a, V, e->ws.eig_w, rows_in_smem, vec_in_smem, vals, mds_scaled,
-                                                  vecs_raw);
-    POST_LAUNCH(e, "k_eig_top8");
-    return 0;
+    // cluster of 8 while the rows fit its shared memory; beyond that a (non-portable) 16-CTA cluster: rows stay
+    // shared-memory resident up to L ~ 650 and, past that, twice as many SMs stream them from L2
+    auto plan = [&](int cl, int& rows_in_smem, int& vec_in_smem, size_t& smem) {
+        const size_t rows = ((n + cl - 1) / cl) * n;
+        size_t big = 0;
+        rows_in_smem = 0; vec_in_smem = 0;
+        if ((7 * n + std::max(rows, vec)) * 8 <= LIMIT) { rows_in_smem = 1; vec_in_smem = 1; big = std::max(rows, vec); }
+        else if ((7 * n + rows) * 8 <= LIMIT) { rows_in_smem = 1; big = rows; }
+        else if ((7 * n + vec) * 8 <= LIMIT) { vec_in_smem = 1; big = vec; }
+        smem = (7 * n + big) * 8;
+    };
+    int r8, v8, r16, v16;
+    size_t s8, s16;
+    plan(8, r8, v8, s8);
+    if (r8) return launch_eig<8>(e, m, L, r8, v8, s8, vals, mds_scaled, vecs_raw, st);
+    plan(16, r16, v16, s16);
+    if (s16 > LIMIT) return e->fail(DMP2_ERR_UNSUPPORTED, "eig_top8: L too large");
+    if (!e->eig_no_cl16) {
+        if (launch_eig<16>(e, m, L, r16, v16, s16, vals, mds_scaled, vecs_raw, st) == 0) return 0;
+        cudaGetLastError();                              // 16-CTA clusters not schedulable here: use 8 from now on
+        e->eig_no_cl16 = true;
+        e->status = 0;
+        e->err.clear();
+    }
+    if (s8 > LIMIT) return e->fail(DMP2_ERR_UNSUPPORTED, "eig_top8: L too large");
+    return launch_eig<8>(e, m, L, r8, v8, s8, vals, mds_scaled, vecs_raw, st);
 }

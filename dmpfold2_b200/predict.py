@@ -73,6 +73,20 @@ def read_aln(input_file: str) -> List[str]:
     return aln
 
 
+def a3m_to_aln(a3m_path: str, aln_path: str) -> int:
+    """The README's `grep -v '^>' file.a3m | sed -e 's/[a-z]//g' > file.aln` (reference README.md:30-33): drop
+    header lines and the lower-case insertion columns of an hhblits a3m.  Returns the number of sequences."""
+    import re
+    n = 0
+    with open(a3m_path, 'r') as fi, open(aln_path, 'w') as fo:
+        for line in fi:
+            if line.startswith('>'):
+                continue
+            fo.write(re.sub('[a-z]', '', line))
+            n += 1
+    return n
+
+
 def encode_aln(aln: List[str]) -> np.ndarray:
     """predict.py:124-132 -- uint8 (N,L) residue codes; N truncated to the first 3000 rows."""
     nseqs, length = len(aln), len(aln[0])

@@ -162,3 +162,14 @@ def test_cfg2_full_size_vs_oracle(eng, oracle, pf10963):
     ref_c, ref_f = oracle.fold(msa, iterations=10, minsteps=100)
     coords, conf = eng.fold_host(msa, None, 10, 100)
     _check(coords, conf, {'coords': ref_c.numpy(), 'confs': ref_f.numpy()}, tol=1e-2)
+
+
+@pytest.mark.parametrize('l,n', [(8, 2), (9, 1), (17, 3)])
+def test_minimal_sizes_vs_oracle(eng, oracle, pf10963, l, n):
+    """Smallest legal shapes: L = 8 is the minimum (top-8 MDS embedding, network.py:250); N = 1 takes the zero-feature
+    branch (predict.py:139)."""
+    msa = np.ascontiguousarray(pf10963[:n, 20:20 + l])
+    ref_c, ref_f = oracle.fold(msa, iterations=1, minsteps=5)
+    eng.set_conv_mode('f16f8')
+    coords, conf = eng.fold_host(msa, None, 1, 5)
+    _check(coords, conf, {'coords': ref_c.numpy(), 'confs': ref_f.numpy()}, tol=2e-3)

@@ -101,3 +101,13 @@ def test_cli_flags_match_reference():
     assert list(sig.parameters) == ['input_file', 'device', 'template', 'iterations', 'minsteps', 'weights_file', 'return_alnmat']
     assert sig.parameters['device'].default == 'cpu' and sig.parameters['iterations'].default == 10
     assert sig.parameters['minsteps'].default == 100
+
+
+def test_a3m_to_aln(tmp_path):
+    from dmpfold2_b200 import predict as P
+    a3m = tmp_path / 'x.a3m'
+    a3m.write_text('>q\nACDEF\n>s1\nACaaDE-\n>s2\n-CDxyzEF\n')
+    out = tmp_path / 'x.aln'
+    assert P.a3m_to_aln(str(a3m), str(out)) == 3
+    assert out.read_text() == 'ACDEF\nACDE-\n-CDEF\n'
+    assert P.encode_aln(P.read_aln(str(out))).shape == (3, 5)
