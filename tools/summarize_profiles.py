@@ -8,23 +8,25 @@ import sys
 
 tag = sys.argv[1] if len(sys.argv) > 1 else 'r3'
 out_tag = sys.argv[2] if len(sys.argv) > 2 else 'round1'
+what = sys.argv[3] if len(sys.argv) > 3 else 'one fold L=300 N=1000 n=1 m=100 (tools/profile_fold.py 1)'
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G = os.path.join(ROOT, 'gpurun_out')
 P = os.path.join(ROOT, 'profiles')
 os.makedirs(P, exist_ok=True)
 
 # ---- launch list -> per-kernel table
-lines = [l for l in open(os.path.join(G, f'{tag}_launches.csv')) if not l.startswith('==')]
+lcsv = os.path.join(G, f'{tag}_launches.csv')
+lines = [l for l in open(lcsv) if not l.startswith('==')] if os.path.isfile(lcsv) else []
 agg = collections.defaultdict(lambda: [0, 0.0])
-for row in csv.DictReader(lines):
+for row in csv.DictReader(lines) if lines else []:
     v = float(row['Metric Value'].replace(',', ''))
     v *= {'ns': 1e-6, 'us': 1e-3, 'ms': 1.0}[row['Metric Unit']]
     k = row['Kernel Name'].split('(')[0][:100]
     agg[k][0] += 1
     agg[k][1] += v
 tot = sum(v[1] for v in agg.values())
-with open(os.path.join(P, f'{out_tag}_launches_summary.txt'), 'w') as fh:
-    fh.write(f'# ncu --metrics gpu__time_duration.sum --clock-control none, one fold L=300 N=1000 n=1 m=100 (tools/profile_fold.py 1)\n')
+with open(os.path.join(P, f'{out_tag}_launches_summary.txt') if agg else os.devnull, 'w') as fh:
+    fh.write(f'# ncu --metrics gpu__time_duration.sum --clock-control none, {what}\n')
     fh.write('# per-launch times are cold-cache and serialised: compare SHARES\n')
     fh.write(f'# total kernel time {tot:.3f} ms over {sum(v[0] for v in agg.values())} launches\n')
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
