@@ -31,19 +31,20 @@ CONV_FLOPS_PER_LAUNCH = 2.0 * L_RES * L_RES * 3200 * 512          # SURVEY.md se
 
 
 def load_weights():
-    from oracle import dmpfold_oracle as O            # only for random_state_dict when the trained files are absent
     wdir = os.path.join(ROOT, 'dmpfold2_b200', 'trained_model')
     if all(os.path.isfile(os.path.join(wdir, f'FINAL_fullmap_e2e_model_part{p}.pt')) for p in (1, 2)):
         from dmpfold2_b200.predict import load_weights as lw
         return lw(None), 'trained DMPfold2 weights'
-    return O.random_state_dict(0), 'random-init weights of the reference architecture (trained files absent)'
+    from dmpfold2_b200.synth import random_state_dict
+    return random_state_dict(0), 'random-init weights of the reference architecture (trained files absent)'
 
 
 def make_msa(seed):
     """Structured synthetic MSA: PF10963 rows/columns resampled to (N_SEQ, L_RES)."""
-    from oracle import dmpfold_oracle as O            # generator + aln encoder only (test infrastructure helpers)
-    base = O.encode_aln(O.read_aln(os.path.join(ROOT, 'tests', 'golden', 'PF10963.aln')))
-    return O.synth_msa_structured(base, L_RES, N_SEQ, seed)
+    from dmpfold2_b200.predict import read_aln, encode_aln
+    from dmpfold2_b200.synth import synth_msa_structured
+    base = encode_aln(read_aln(os.path.join(ROOT, 'tests', 'golden', 'PF10963.aln')))
+    return synth_msa_structured(base, L_RES, N_SEQ, seed)
 
 
 class ClockSampler(threading.Thread):

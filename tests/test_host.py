@@ -111,3 +111,34 @@ def test_a3m_to_aln(tmp_path):
     assert P.a3m_to_aln(str(a3m), str(out)) == 3
     assert out.read_text() == 'ACDEF\nACDE-\n-CDEF\n'
     assert P.encode_aln(P.read_aln(str(out))).shape == (3, 5)
+
+
+def test_product_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing in the shipped package may import it, and bench.py may do so only
+    inside its CPU-baseline leg."""
+    import ast
+    pkg = os.path.join(ROOT, 'dmpfold2_b200')
+    for fn in os.listdir(pkg):
+        if fn.endswith('.py'):
+            tree = ast.parse(open(os.path.join(pkg, fn)).read())
+            for node in ast.walk(tree):
+                if isinstance(node, (ast.Import, ast.ImportFrom)):
+                    names = [a.name for a in node.names] + ([node.module] if isinstance(node, ast.ImportFrom) and node.module else [])
+                    assert not any(n.split('.')[0] == 'oracle' for n in names), f'{fn} imports the oracle'
+    for fn in os.listdir(os.path.join(pkg, 'csrc')):
+        assert 'oracle' not in open(os.path.join(pkg, 'csrc', fn)).read()
+    tree = ast.parse(open(os.path.join(ROOT, 'bench.py')).read())
+    for fdef in [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)]:
+        imports = [n for n in ast.walk(fdef) if isinstance(n, ast.ImportFrom) and n.module and n.module.split('.')[0] == 'oracle']
+        if imports:
+            assert fdef.name == 'cpu_sample', f'bench.py: {fdef.name} imports the oracle'
+    top = [n for n in tree.body if isinstance(n, (ast.Import, ast.ImportFrom))]
+    assert not any(getattr(n, 'module', None) and n.module.startswith('oracle') for n in top)
+
+
+def test_synth_generators_match_the_oracle_copies(pf10963):
+    from dmpfold2_b200 import synth as S
+    assert np.array_equal(S.synth_msa_structured(pf10963, 130, 40, 3), O.synth_msa_structured(pf10963, 130, 40, 3))
+    assert np.array_equal(S.synth_msa_random(40, 12, 5), O.synth_msa_random(40, 12, 5))
+    a, b = S.random_state_dict(1), O.random_state_dict(1)
+    assert set(a) == set(b) and all(torch.equal(a[k], b[k]) for k in a)
