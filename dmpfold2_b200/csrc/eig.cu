@@ -79,7 +79,7 @@ __device__ __forceinline__ double block_sum1(double v, double* scr) {
 template <int EIG_CL>
 __global__ void __launch_bounds__(EIG_THREADS, 1)
 k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* __restrict__ V, double* __restrict__ wk,
-           int rows_in_smem, int vec_in_smem, int mser, float* __restrict__ vals_out, float* __restrict__ mds_out,
+           int rows_in_smem, int vec_in_smem, float* __restrict__ vals_out, float* __restrict__ mds_out,
            float* __restrict__ vec_out) {
     cg::cluster_group cluster = cg::this_cluster();
     const int c = (int)cluster.block_rank();
@@ -140,10 +140,8 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
     }
     cluster.sync();
     uint32_t gph = 0;                                             // phase parity bits of the four barriers
-    int kser = -1;                                                // first column handled by the single-CTA tail
     for (int k = 0; k < n - 2; k++) {
         const int m = n - k - 1;                       // length of the column below the diagonal
-        if (mser > 0 && n - k <= mser) { kser = k; break; }
         const int pp = k & 1;
         double* sv = svb + pp * n;
         double* sp = spb + pp * n;
@@ -207,87 +205,6 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
         }
         __syncthreads();
     }
-    if (kser >= 0) {
-        // ---------------- 1b. single-CTA tail ----------------------------------------------------------
-        // Once the trailing matrix (ns x ns, ns = n - kser <= mser) fits one CTA's shared memory, the per-column cost
-        // of the cluster exchange (two ~1 us DSMEM round trips) exceeds the arithmetic: gather it into CTA 0 and finish
-        // there with block barriers only.  The gather target overlays CTA 0's row storage, so CTA 0 first parks its own
-        // live elements in registers.
-        const int ns = n - kser;
-        double* S = big;                                          // [ns][ns] in CTA 0
-        double keep[8];
-        int nkeep = 0;
-        cluster.sync();                                           // all updates of column kser-1 are done
-        const int lif = (kser - c + EIG_CL - 1) / EIG_CL;         // first local row with global index >= kser
-        const int nlive = (nloc - lif) * ns;                      // live elements of this CTA
-        if (c == 0)
-            for (int t = tid; t < nlive; t += EIG_THREADS) {
-                const int li = lif + t / ns, j = t % ns;
-                keep[nkeep++] = rbase[li * rstride + kser + j];
-            }
-        cluster.sync();                                           // CTA 0's rows are parked: S may be overwritten
-        {
-            double* S0 = cluster.map_shared_rank(S, 0);
-            int q = 0;
-            for (int t = tid; t < nlive; t += EIG_THREADS) {
-                const int li = lif + t / ns, j = t % ns;
-                const int i = li * EIG_CL + c - kser;
-                S0[i * ns + j] = (c == 0) ? keep[q++] : rbase[li * rstride + kser + j];
-            }
-        }
-        cluster.sync();                                           // S complete
-        if (c == 0) {
-            double* sv = svb;
-            double* sp = spb;
-            for (int k = kser; k < n - 2; k++) {
-                const int m = n - k - 1, o = k - kser;            // trailing block starts at S[o+1][o+1]
-                double part = 0.0;
-                for (int i = tid; i < m; i += EIG_THREADS) { const double x = S[(o + 1 + i) * ns + o]; sv[i] = x; part += x * x; }
-                if (tid == 0) gd[k] = S[o * ns + o];
-                const double sigma = block_sum1(part, scr_a);     // (barrier inside: sv complete)
-                const double x0 = sv[0];
-                const double tail = sigma - x0 * x0;
-                const bool reflect = tail > 0.0;
-                const double alpha = reflect ? ((x0 >= 0.0) ? -sqrt(sigma) : sqrt(sigma)) : x0;
-                const double v0 = x0 - alpha;
-                const double bt = reflect ? 2.0 / (tail + v0 * v0) : 0.0;
-                if (tid == 0) { ge[k] = alpha; beta[k] = bt; }
-                for (int i = tid; i < m; i += EIG_THREADS) V[(int64_t)k * n + i] = i == 0 ? v0 : sv[i];
-                for (int i = warp; i < m; i += NW) {
-                    const double* row = S + (o + 1 + i) * ns + (o + 1);
-                    double acc = lane == 0 ? row[0] * v0 : 0.0, acc2 = 0.0;
-                    int j = lane == 0 ? 32 : lane;
-                    for (; j + 32 < m; j += 64) { acc += row[j] * sv[j]; acc2 += row[j + 32] * sv[j + 32]; }
-                    if (j < m) acc += row[j] * sv[j];
-                    acc = warp_sum(acc + acc2) * bt;
-                    if (lane == 0) sp[i] = acc;
-                }
-                __syncthreads();
-                double pv = 0.0;
-                for (int i = tid; i < m; i += EIG_THREADS) pv += sp[i] * (i == 0 ? v0 : sv[i]);
-                const double kk = 0.5 * bt * block_sum1(pv, scr_b);
-                if (reflect) {
-                    for (int i = warp; i < m; i += NW) {
-                        double* row = S + (o + 1 + i) * ns + (o + 1);
-                        const double vi = i == 0 ? v0 : sv[i];
-                        const double wi = sp[i] - kk * vi;
-#pragma unroll 4
-                        for (int j = lane; j < m; j += 32) {
-                            const double vj = j == 0 ? v0 : sv[j];
-                            row[j] -= vi * (sp[j] - kk * vj) + wi * vj;
-                        }
-                    }
-                }
-                __syncthreads();
-            }
-            if (tid == 0) {
-                gd[n - 2] = S[(ns - 2) * ns + (ns - 2)];
-                gd[n - 1] = S[(ns - 1) * ns + (ns - 1)];
-                ge[n - 2] = S[(ns - 1) * ns + (ns - 2)];
-                ge[n - 1] = 0.0;
-            }
-        }
-    } else
     if (tid == 0) {
         for (int i = n - 2; i < n; i++)
             if (i >= 0 && (i % EIG_CL) == c) gd[i] = rbase[(i / EIG_CL) * rstride + i];
@@ -510,7 +427,7 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
 }
 
 template <int CL>
-static int launch_eig(dmp2_engine* e, const float* m, int L, int rows_in_smem, int vec_in_smem, int mser, size_t smem, float* vals,
+static int launch_eig(dmp2_engine* e, const float* m, int L, int rows_in_smem, int vec_in_smem, size_t smem, float* vals,
                       float* mds_scaled, float* vecs_raw, cudaStream_t st) {
     double* V = e->ws.eig_a + (int64_t)L * L;
     cudaLaunchConfig_t cfg = {};
@@ -523,7 +440,7 @@ static int launch_eig(dmp2_engine* e, const float* m, int L, int rows_in_smem, i
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    CUDA_TRY(e, cudaLaunchKernelEx(&cfg, k_eig_top8<CL>, m, L, e->ws.eig_a, V, e->ws.eig_w, rows_in_smem, vec_in_smem, mser, vals,
+    CUDA_TRY(e, cudaLaunchKernelEx(&cfg, k_eig_top8<CL>, m, L, e->ws.eig_a, V, e->ws.eig_w, rows_in_smem, vec_in_smem, vals,
                                    mds_scaled, vecs_raw));
     POST_LAUNCH(e, "k_eig_top8");
     return 0;
@@ -541,35 +458,28 @@ int run_eig_top8(dmp2_engine* e, const float* m, int L, float* vals, float* mds_
     const size_t vec = 32 * n;
     // cluster of 8 while the rows fit its shared memory; beyond that a (non-portable) 16-CTA cluster: rows stay
     // shared-memory resident up to L ~ 650 and, past that, twice as many SMs stream them from L2
-    // mser: size of the trailing matrix finished by CTA 0 alone (needs mser^2 doubles of shared memory there and
-    // at most 8 parked elements per thread: ceil(mser / cl) * mser <= 8 * EIG_THREADS)
-    auto plan = [&](int cl, int& rows_in_smem, int& vec_in_smem, int& mser, size_t& smem) {
+    auto plan = [&](int cl, int& rows_in_smem, int& vec_in_smem, size_t& smem) {
         const size_t rows = ((n + cl - 1) / cl) * n;
         size_t big = 0;
-        rows_in_smem = 0; vec_in_smem = 0; mser = 0;
+        rows_in_smem = 0; vec_in_smem = 0;
         if ((7 * n + std::max(rows, vec)) * 8 <= LIMIT) { rows_in_smem = 1; vec_in_smem = 1; big = std::max(rows, vec); }
         else if ((7 * n + rows) * 8 <= LIMIT) { rows_in_smem = 1; big = rows; }
         else if ((7 * n + vec) * 8 <= LIMIT) { vec_in_smem = 1; big = vec; }
-        {
-            size_t ms = std::min<size_t>(n, 256);
-            while (ms > 8 && ((7 * n + std::max(big, ms * ms)) * 8 > LIMIT || ((ms + cl - 1) / cl) * ms > (size_t)8 * EIG_THREADS)) ms--;
-            if (ms > 8) { mser = (int)ms; big = std::max(big, ms * ms); }
-        }
         smem = (7 * n + big) * 8;
     };
-    int r8, v8, m8, r16, v16, m16;
+    int r8, v8, r16, v16;
     size_t s8, s16;
-    plan(8, r8, v8, m8, s8);
-    if (r8) return launch_eig<8>(e, m, L, r8, v8, m8, s8, vals, mds_scaled, vecs_raw, st);
-    plan(16, r16, v16, m16, s16);
+    plan(8, r8, v8, s8);
+    if (r8) return launch_eig<8>(e, m, L, r8, v8, s8, vals, mds_scaled, vecs_raw, st);
+    plan(16, r16, v16, s16);
     if (s16 > LIMIT) return e->fail(DMP2_ERR_UNSUPPORTED, "eig_top8: L too large");
     if (!e->eig_no_cl16) {
-        if (launch_eig<16>(e, m, L, r16, v16, m16, s16, vals, mds_scaled, vecs_raw, st) == 0) return 0;
+        if (launch_eig<16>(e, m, L, r16, v16, s16, vals, mds_scaled, vecs_raw, st) == 0) return 0;
         cudaGetLastError();                              // 16-CTA clusters not schedulable here: use 8 from now on
         e->eig_no_cl16 = true;
         e->status = 0;
         e->err.clear();
     }
     if (s8 > LIMIT) return e->fail(DMP2_ERR_UNSUPPORTED, "eig_top8: L too large");
-    return launch_eig<8>(e, m, L, r8, v8, m8, s8, vals, mds_scaled, vecs_raw, st);
+    return launch_eig<8>(e, m, L, r8, v8, s8, vals, mds_scaled, vecs_raw, st);
 }
