@@ -8,6 +8,7 @@
 //   3. inverse iteration + Gram-Schmidt, 4. back-transformation                      }
 //   5. canonical sign (largest-|component| positive, lowest index wins ties), sqrt(clamp(relu(l),1e-8)) scaling.
 #include "common.cuh"
+#include <stdlib.h>
 #include "cluster_comm.cuh"
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
@@ -470,7 +471,8 @@ int run_eig_top8(dmp2_engine* e, const float* m, int L, float* vals, float* mds_
     int r8, v8, r16, v16;
     size_t s8, s16;
     plan(8, r8, v8, s8);
-    if (r8) return launch_eig<8>(e, m, L, r8, v8, s8, vals, mds_scaled, vecs_raw, st);
+    static const bool force16 = getenv("DMP2_EIG_CL") && atoi(getenv("DMP2_EIG_CL")) == 16;   // tuning knob
+    if (r8 && !force16) return launch_eig<8>(e, m, L, r8, v8, s8, vals, mds_scaled, vecs_raw, st);
     plan(16, r16, v16, s16);
     if (s16 > LIMIT) return e->fail(DMP2_ERR_UNSUPPORTED, "eig_top8: L too large");
     if (!e->eig_no_cl16) {

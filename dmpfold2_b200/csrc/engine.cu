@@ -271,8 +271,8 @@ int ensure_workspace(dmp2_engine* e, int L, int N) {
     TRY(wsalloc(e, &ws.x8hi, P * 128));
     TRY(wsalloc(e, &ws.stat_part, (int64_t)e->num_sms * 4 * 256));
     TRY(wsalloc(e, &ws.norm_ss, 256));
-    TRY(wsalloc(e, &ws.ticket, 4));
-    CUDA_TRY(e, cudaMemset(ws.ticket, 0, 16));
+    TRY(wsalloc(e, &ws.ticket, 64));
+    CUDA_TRY(e, cudaMemset(ws.ticket, 0, 64 * sizeof(unsigned int)));
     TRY(wsalloc(e, &ws.head, 2 * P));
     TRY(wsalloc(e, &ws.conf, L));
     TRY(wsalloc(e, &ws.mmat, P));

@@ -91,28 +91,44 @@ __global__ void __launch_bounds__(512) k_in_stats(const float* __restrict__ raw,
         for (int g = 0; g < 16; g++) t += sh[g][threadIdx.x];
         part[(int64_t)blockIdx.x * 256 + threadIdx.x] = t;
     }
+    // Deterministic two-level fold of the per-CTA partials: the last CTA of every group of 16 folds its group (fixed
+    // order), the last group to finish folds the group sums.  The serial tail is 16 + #groups loads instead of #CTAs.
+    const unsigned G = 16, grp_id = blockIdx.x / G, ngrp = (gridDim.x + G - 1) / G;
+    const unsigned gfirst = grp_id * G, gsize = min(G, gridDim.x - gfirst);
+    double* part2 = part + (int64_t)gridDim.x * 256;
     __threadfence();
-    __shared__ bool last;
+    __shared__ int stage;                              // 0 = not last in group, 1 = last in group, 2 = last overall
     __syncthreads();
-    if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    if (threadIdx.x == 0) stage = (atomicAdd(ticket + 1 + grp_id, 1u) == gsize - 1) ? 1 : 0;
     __syncthreads();
-    if (!last) return;
+    if (stage == 0) return;
     __threadfence();
-    // fixed-order fold of the CTA partials: 2 threads per column, then a fixed combine
-    {
-        const int col = threadIdx.x & 255, q = threadIdx.x >> 8;
+    if (threadIdx.x < 256) {
+        double t = 0;
+#pragma unroll 16
+        for (unsigned b = 0; b < gsize; b++) t += part[(int64_t)(gfirst + b) * 256 + threadIdx.x];
+        part2[(int64_t)grp_id * 256 + threadIdx.x] = t;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ticket[1 + grp_id] = 0;
+        stage = (atomicAdd(ticket, 1u) == ngrp - 1) ? 2 : 1;
+    }
+    __syncthreads();
+    if (stage != 2) return;
+    __threadfence();
+    if (threadIdx.x < 256) {
         double t = 0;
 #pragma unroll 8
-        for (unsigned b = q; b < gridDim.x; b += 2) t += part[(int64_t)b * 256 + col];
-        sh[q][col] = t;
+        for (unsigned b = 0; b < ngrp; b++) t += part2[(int64_t)b * 256 + threadIdx.x];
+        sh[0][threadIdx.x] = t;
     }
     __syncthreads();
     if (threadIdx.x < 128) {
         const int c = threadIdx.x;
-        double sum = sh[0][c] + sh[1][c];
-        double sq = sh[0][128 + c] + sh[1][128 + c];
-        double mean = sum / (double)npix;
-        double var = sq / (double)npix - mean * mean;
+        double mean = sh[0][c] / (double)npix;
+        double var = sh[0][128 + c] / (double)npix - mean * mean;
         if (var < 0) var = 0;
         norm[c] = (float)mean;
         norm[128 + c] = (float)((double)gamma[c] / sqrt(var + 1e-5));
