@@ -137,6 +137,22 @@ def aln_to_coords(input_file, device=default_device, template=None, iterations=d
     return coords, confs
 
 
+def alns_to_coords(input_files, device='cuda', templates=None, iterations=default_iterations, minsteps=default_minsteps,
+                   weights_file=None, gather=True):
+    """Batch form of aln_to_coords for many independent alignments (BASELINE.json configs[2]).  Under
+    torch.distributed (one process per GPU) the list is sharded round-robin over the ranks with no data-path
+    collective (dmpfold2_b200.parallel.fold_many); results come back as CPU tensors in input order."""
+    from .parallel import fold_many
+    templates = templates or [None] * len(input_files)
+
+    def one(job):
+        path, tmpl = job
+        coords, confs = aln_to_coords(path, device=device, template=tmpl, iterations=iterations, minsteps=minsteps,
+                                      weights_file=weights_file)
+        return coords.cpu(), confs.cpu()
+    return fold_many(list(zip(input_files, templates)), one, gather=gather)
+
+
 _RNAMES = {0: 'ALA', 1: 'ARG', 2: 'ASN', 3: 'ASP', 4: 'CYS', 5: 'GLN', 6: 'GLU', 7: 'GLY', 8: 'HIS', 9: 'ILE', 10: 'LEU',
            11: 'LYS', 12: 'MET', 13: 'PHE', 14: 'PRO', 15: 'SER', 16: 'THR', 17: 'TRP', 18: 'TYR', 19: 'VAL'}
 

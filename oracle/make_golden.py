@@ -94,6 +94,20 @@ def main():
     np.savez_compressed(os.path.join(GOLD, 'pf10963_n0_m0.npz'), **out)
     print('n0m0 mean conf', float(confs.mean()))
 
+    # ---- the CLI's stdout for the same n=0, m=0 run (predict.py:195-208), for the PDB-writer byte-exactness test
+    import contextlib
+    import io
+    buf = io.StringIO()
+    argv = sys.argv
+    sys.argv = ['dmpfold', '-i', aln, '-n', '0', '-m', '0']
+    try:
+        with contextlib.redirect_stdout(buf):
+            dmpfold.run_dmpfold()
+    finally:
+        sys.argv = argv
+    with open(os.path.join(GOLD, 'pf10963_n0_m0.pdb'), 'w') as fh:
+        fh.write(buf.getvalue())
+
     for n, m in ((2, 20), (10, 100)):
         c, f = dmpfold.aln_to_coords(aln, iterations=n, minsteps=m)
         np.savez_compressed(os.path.join(GOLD, f'pf10963_n{n}_m{m}.npz'), coords=c.numpy(), confs=f.numpy())

@@ -173,3 +173,17 @@ def test_minimal_sizes_vs_oracle(eng, oracle, pf10963, l, n):
     eng.set_conv_mode('f16f8')
     coords, conf = eng.fold_host(msa, None, 1, 5)
     _check(coords, conf, {'coords': ref_c.numpy(), 'confs': ref_f.numpy()}, tol=2e-3)
+
+
+@needs_weights
+def test_batch_api(pf10963, tmp_path):
+    from dmpfold2_b200 import alns_to_coords, aln_to_coords
+    aln = os.path.join(GOLDEN, 'PF10963.aln')
+    short = tmp_path / 'short.aln'
+    with open(aln) as fh:
+        rows = [l.rstrip()[:40] for l in fh.readlines()[:30]]
+    short.write_text('\\n'.join(rows) + '\\n')
+    res = alns_to_coords([aln, str(short)], device='cuda:0', iterations=1, minsteps=5)
+    assert len(res) == 2 and res[0][0].shape == (82, 5, 3) and res[1][0].shape == (40, 5, 3)
+    c, f = aln_to_coords(str(short), device='cuda:0', iterations=1, minsteps=5)
+    assert torch.equal(res[1][0], c.cpu()) and torch.equal(res[1][1], f.cpu())

@@ -142,3 +142,13 @@ def test_synth_generators_match_the_oracle_copies(pf10963):
     assert np.array_equal(S.synth_msa_random(40, 12, 5), O.synth_msa_random(40, 12, 5))
     a, b = S.random_state_dict(1), O.random_state_dict(1)
     assert set(a) == set(b) and all(torch.equal(a[k], b[k]) for k in a)
+
+
+def test_pdb_writer_is_byte_exact_against_the_reference_cli():
+    """format_pdb on the reference's own coordinates must reproduce the reference CLI's stdout byte for byte
+    (fixture written by oracle/make_golden.py from `dmpfold -i PF10963.aln -n 0 -m 0`)."""
+    from dmpfold2_b200 import predict as P
+    g = np.load(os.path.join(GOLDEN, 'pf10963_n0_m0.npz'))
+    want = open(os.path.join(GOLDEN, 'pf10963_n0_m0.pdb')).read()
+    got = P.format_pdb(torch.from_numpy(g['coords']), torch.from_numpy(g['confs']), g['alnmat'])
+    assert got == want
