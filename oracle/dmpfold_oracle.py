@@ -93,11 +93,11 @@ def fast_dca(msa1hot: torch.Tensor, weights: torch.Tensor, penalty: float = 4.5)
     mean = (x * weights[:, None]).sum(dim=0, keepdim=True) / num_points
     x = (x - mean) * torch.sqrt(weights[:, None])
     cov = (x.t() @ x) / num_points
-    cov_reg = cov + torch.eye(nc * ns) * penalty / torch.sqrt(weights.sum())
+    cov_reg = cov + torch.eye(nc * ns, device=x.device) * penalty / torch.sqrt(weights.sum())
     inv_cov = torch.linalg.inv(cov_reg)
     x1 = inv_cov.view(nc, ns, nc, ns)
     features = x1.transpose(1, 2).contiguous().reshape(nc, nc, ns * ns)
-    eye = torch.eye(nc)
+    eye = torch.eye(nc, device=x.device)
     x3 = torch.sqrt((x1[:, :-1, :, :-1] ** 2).sum(dim=(1, 3))) * (1 - eye)
     apc = x3.sum(dim=0, keepdim=True) * x3.sum(dim=1, keepdim=True) / x3.sum()
     contacts = (x3 - apc) * (1 - eye)
@@ -111,7 +111,7 @@ def msa_features(msa: torch.Tensor) -> torch.Tensor:
     w = reweight(hot, 0.8)
     if nseqs > 1:
         return fast_dca(hot, w).float()
-    return torch.zeros((length, length, 442))
+    return torch.zeros((length, length, 442), device=msa.device)
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -131,7 +131,7 @@ def gru_layer(x: torch.Tensor, w_ih, w_hh, b_ih, b_hh, reverse: bool = False) ->
     t_len, b, _ = x.shape
     hs = w_hh.shape[1]
     gi_all = x @ w_ih.t() + b_ih
-    h = torch.zeros((b, hs))
+    h = torch.zeros((b, hs), device=x.device)
     out = [None] * t_len
     order = range(t_len - 1, -1, -1) if reverse else range(t_len)
     for t in order:
@@ -156,7 +156,7 @@ def _nn_gru(sd: Dict[str, torch.Tensor], prefix: str, inp: int, hid: int, layers
     """torch.nn.GRU loaded with the reference weights -- the same ATen kernel the reference runs
     (used for the full-size oracle and the CPU baseline timing; gru_stack above is its restatement)."""
     g = torch.nn.GRU(inp, hid, num_layers=layers, bidirectional=bidir)
-    g.load_state_dict({k[len(prefix) + 1:]: v for k, v in sd.items() if k.startswith(prefix + '.')})
+    g.load_state_dict({k[len(prefix) + 1:]: v.cpu() for k, v in sd.items() if k.startswith(prefix + '.')})
     return g.eval()
 
 
@@ -292,11 +292,14 @@ def calpha_to_main_chain(ca: torch.Tensor) -> torch.Tensor:
 class Oracle:
     """Holds the weights (a state_dict as loaded by predict.py:89-92) and runs the reference algorithm."""
 
-    def __init__(self, state_dict: Dict[str, torch.Tensor]):
-        self.sd = {k: v.detach().float().cpu() for k, v in state_dict.items()}
-        self._vgru = _nn_gru(self.sd, 'vgru', 22, 512, 2, False)
-        self._hgru = _nn_gru(self.sd, 'hgru', 512, 256, 2, True)
-        self._cgru = _nn_gru(self.sd, 'coord_gru', 520, 256, 3, True)
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device: str = 'cpu'):
+        # device='cpu' is the oracle proper.  A cuda device only serves tools/torch_cuda_bar.py, which times the same
+        # algorithm on PyTorch's library kernels (cuDNN/cuBLAS/cuSOLVER) as the "existing Blackwell kernels" bar.
+        self.device = torch.device(device)
+        self.sd = {k: v.detach().float().to(self.device) for k, v in state_dict.items()}
+        self._vgru = _nn_gru(self.sd, 'vgru', 22, 512, 2, False).to(self.device)
+        self._hgru = _nn_gru(self.sd, 'hgru', 512, 256, 2, True).to(self.device)
+        self._cgru = _nn_gru(self.sd, 'coord_gru', 520, 256, 3, True).to(self.device)
 
     # -- 1-D track: network.py:223-226
     def mat1d(self, msa: torch.Tensor) -> torch.Tensor:
@@ -356,15 +359,15 @@ class Oracle:
     def fold(self, msa: np.ndarray, template_ca: Optional[np.ndarray] = None, iterations: int = 10,
              minsteps: int = 100, taps: Optional[dict] = None) -> Tuple[torch.Tensor, torch.Tensor]:
         """predict.py:121-153 given the encoded alignment.  Returns coords (L,5,3), confs (L,)."""
-        msa_t = torch.from_numpy(np.ascontiguousarray(msa)).long()
+        msa_t = torch.from_numpy(np.ascontiguousarray(msa)).long().to(self.device)
         length = msa_t.shape[1]
         with torch.no_grad():
             feats = msa_features(msa_t).permute(2, 0, 1).unsqueeze(0)
             if template_ca is not None:
-                c = torch.from_numpy(template_ca).float().unsqueeze(0)
+                c = torch.from_numpy(template_ca).float().unsqueeze(0).to(self.device)
                 dmap = (c - c.transpose(0, 1)).pow(2).sum(dim=2).sqrt()[None, None]
             else:
-                dmap = torch.zeros((1, 1, length, length)) - 1
+                dmap = torch.zeros((1, 1, length, length), device=self.device) - 1
             x2 = torch.cat((feats, dmap), dim=1)
             if taps is not None:
                 taps['x2'] = x2
