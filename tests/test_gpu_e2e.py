@@ -182,7 +182,7 @@ def test_batch_api(pf10963, tmp_path):
     short = tmp_path / 'short.aln'
     with open(aln) as fh:
         rows = [l.rstrip()[:40] for l in fh.readlines()[:30]]
-    short.write_text('\\n'.join(rows) + '\\n')
+    short.write_text('\n'.join(rows) + '\n')
     res = alns_to_coords([aln, str(short)], device='cuda:0', iterations=1, minsteps=5)
     assert len(res) == 2 and res[0][0].shape == (82, 5, 3) and res[1][0].shape == (40, 5, 3)
     c, f = aln_to_coords(str(short), device='cuda:0', iterations=1, minsteps=5)
