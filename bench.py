@@ -288,6 +288,8 @@ def main():
             'roofline': {'bound': 'tensor', 'kernel': 'k_conv5_tc', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s',
                          'frac': achieved / peak_tf, 'traffic': traffic, 'launches_timed': n_conv,
                          'avg_launch_ms': avg_conv_ms, 'conv_share_of_step': conv_ms / dev_ms, 'peak_source': peak_src,
+                         'mma_fp16_equivalents_per_mac': {'f16f8': 2.0, 'f16x3': 3.0, 'f16': 1.0}.get(args.conv_mode),
+                         'mma_equivalent_tflops': achieved * {'f16f8': 2.0, 'f16x3': 3.0, 'f16': 1.0}.get(args.conv_mode, 1.0),
                          'note': 'algorithmic FLOPs 2*L^2*3200*512 per launch; f16x3 issues 3 fp16 MMAs per algorithmic MAC, '
                                  'f16f8 one fp16 MMA + two fp8 MMAs (2 fp16-equivalents)'},
             'stage_ms_last_e2e_step': stages,
