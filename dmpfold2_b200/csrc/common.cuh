@@ -126,6 +126,10 @@ struct Workspace {
     float* vg_h = nullptr;         // [2 layers][2 buffers][L][512]
     __half* vt_h16 = nullptr;      // [4 buffers][hi|lo][L][512] fp16 split of the vgru states
     float* vt_gi1 = nullptr;       // [2][L][1536] layer-1 input projections in flight
+    __half* vp_h16 = nullptr;      // persistent vgru: [h0_hi 4][h0_lo 4][h1_hi 2][h1_lo 2] x [L][512]
+    float* vp_f32 = nullptr;       // persistent vgru: [h0 4][h1 2] x [L][512]
+    float* vp_gi1 = nullptr;       // persistent vgru: [4][L][1536]
+    unsigned int* vp_cnt = nullptr; // persistent vgru: [row tiles][3] progress counters
     float* v_last = nullptr;       // [L][512]
     float* gi = nullptr;           // [L][1536] input projections of the current bi-GRU layer
     float* seq_a = nullptr;        // [L][520] layer input / output ping
@@ -176,8 +180,9 @@ struct dmp2_engine {
     float stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     void* tc_state = nullptr;        // tensor-core conv state (tensor maps), owned by conv_tc.cu
     void* vt_state = nullptr;        // tensor-core vgru state, owned by vgru_tc.cu
+    void* vp_state = nullptr;        // persistent tensor-core vgru state, owned by vgru_persist.cu
     int conv_cluster = 2;            // CTAs per cluster sharing the conv weight stream by TMA multicast (1 = off)
-    int vgru_mode = 0;               // 0 = tensor cores (fp16x3), 1 = CUDA-core fp32 validation path
+    int vgru_mode = 0;               // 0 = tensor cores, one launch per MSA row; 1 = CUDA-core fp32 validation path; 2 = tensor cores, persistent kernel
     bool eig_no_cl16 = false;        // set when a 16-CTA cluster launch was refused
     bool attr_eig = false, attr_refine = false;   // per-engine (= per-device) cudaFuncSetAttribute done
     bool profile = false;            // record a CUDA-event pair around every conv launch (bench.py roofline)
@@ -204,6 +209,8 @@ int run_vgru(dmp2_engine* e, const uint8_t* msa, int N, int L, float* out, cudaS
 int run_vgru_ffma(dmp2_engine* e, const uint8_t* msa, int N, int L, float* out, cudaStream_t st);
 int run_vgru_tc(dmp2_engine* e, const uint8_t* msa, int N, int L, float* out, cudaStream_t st);
 void vgru_tc_destroy(dmp2_engine* e);
+int run_vgru_persist(dmp2_engine* e, const uint8_t* msa, int N, int L, float* out, cudaStream_t st);
+void vgru_persist_destroy(dmp2_engine* e);
 int run_bigru(dmp2_engine* e, const BiGruLayer* layers, int nlayers, const float* in, int L, float* out, cudaStream_t st);
 int run_coord_head(dmp2_engine* e, const float* mat1d_t, const float* mds, int L, float* ca, cudaStream_t st);
 // resnet.cu

@@ -256,6 +256,10 @@ int ensure_workspace(dmp2_engine* e, int L, int N) {
     TRY(wsalloc(e, &ws.vg_h, 4 * (int64_t)L * 512));
     TRY(wsalloc(e, &ws.vt_h16, 8 * (int64_t)L * 512));
     TRY(wsalloc(e, &ws.vt_gi1, 2 * (int64_t)L * 1536));
+    TRY(wsalloc(e, &ws.vp_h16, 12 * (int64_t)L * 512));
+    TRY(wsalloc(e, &ws.vp_f32, 6 * (int64_t)L * 512));
+    TRY(wsalloc(e, &ws.vp_gi1, 4 * (int64_t)L * 1536));
+    TRY(wsalloc(e, &ws.vp_cnt, 3 * (int64_t)((L + 127) / 128)));
     TRY(wsalloc(e, &ws.v_last, (int64_t)L * 512));
     TRY(wsalloc(e, &ws.gi, (int64_t)L * 1536));
     TRY(wsalloc(e, &ws.seq_a, (int64_t)L * 520));
@@ -406,6 +410,8 @@ int dmp2_create(dmp2_engine** out, int device, int n_tensors, const char* const*
     if (cc && !strcmp(cc, "pair")) e->conv_cluster = 0;        // cta_group::2 CTA-pair kernel
     const char* vm = getenv("DMP2_VGRU");
     if (vm && !strcmp(vm, "ffma")) e->vgru_mode = 1;
+    if (vm && !strcmp(vm, "persist")) e->vgru_mode = 2;
+    if (vm && !strcmp(vm, "steps")) e->vgru_mode = 0;
     *out = e;
     return 0;
 }
@@ -416,6 +422,7 @@ void dmp2_destroy(dmp2_engine* e) {
     cudaDeviceSynchronize();
     conv_tc_destroy(e);
     vgru_tc_destroy(e);
+    vgru_persist_destroy(e);
     free_workspace(e);
     for (void* p : e->weight_allocs) cudaFree(p);
     if (e->ev_ok) for (int i = 0; i < 16; i++) cudaEventDestroy(e->ev[i]);

@@ -22,7 +22,7 @@ constexpr int VT_B_BYTES = VT_N * 64 * 2;      // 12 KB
 constexpr int VT_STAGE_BYTES = 2 * VT_A_BYTES + 2 * VT_B_BYTES;     // 56 KB
 constexpr int VT_STAGES = 4;
 constexpr int VT_SMEM = VT_STAGES * VT_STAGE_BYTES + 1024 + 256;
-constexpr int VT_THREADS = 320;             // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (2 per TMEM lane quarter)
+constexpr int VT_THREADS = 576;             // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue (4 per TMEM lane quarter, 8 units each)
 
 struct VtMaps {
     CUtensorMap a_hi[4], a_lo[4];              // h buffers: 0,1 = h0 ping/pong, 2,3 = h1 ping/pong
@@ -92,7 +92,6 @@ __global__ void __launch_bounds__(VT_THREADS, 1) k_vgru_step(const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
-    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     if (warp == 0) {
         if (lane == 0) {
@@ -100,15 +99,28 @@ __global__ void __launch_bounds__(VT_THREADS, 1) k_vgru_step(const __grid_consta
             const CUtensorMap* al = &maps.a_lo[R.a_sel];
             const CUtensorMap* bh = &maps.b_hi[role_id];
             const CUtensorMap* bl = &maps.b_lo[role_id];
+            // The weights do not depend on the previous step: fill the B half of every ring stage before the
+            // dependency wait (byte count raised without arriving, so the stage stays open until its A half is issued).
+            for (int kb = 0; kb < VT_STAGES; kb++) {
+                const uint32_t st = base + kb * VT_STAGE_BYTES;
+                mbar_add_tx(full(kb), 2 * VT_B_BYTES);
+                tma_load_2d(st + 2 * VT_A_BYTES, bh, full(kb), kb * 64, slice * VT_N);
+                tma_load_2d(st + 2 * VT_A_BYTES + VT_B_BYTES, bl, full(kb), kb * 64, slice * VT_N);
+            }
+            asm volatile("griddepcontrol.wait;" ::: "memory");
             int s = 0, ph = 0;
             for (int kb = 0; kb < VT_NKB; kb++) {
                 mbar_wait(empty(s), ph ^ 1);
-                mbar_expect_tx(full(s), VT_STAGE_BYTES);
                 const uint32_t st = base + s * VT_STAGE_BYTES;
+                if (kb < VT_STAGES) {
+                    mbar_expect_tx(full(s), 2 * VT_A_BYTES);
+                } else {
+                    mbar_expect_tx(full(s), VT_STAGE_BYTES);
+                    tma_load_2d(st + 2 * VT_A_BYTES, bh, full(s), kb * 64, slice * VT_N);
+                    tma_load_2d(st + 2 * VT_A_BYTES + VT_B_BYTES, bl, full(s), kb * 64, slice * VT_N);
+                }
                 tma_load_2d(st, ah, full(s), kb * 64, m0);
                 tma_load_2d(st + VT_A_BYTES, al, full(s), kb * 64, m0);
-                tma_load_2d(st + 2 * VT_A_BYTES, bh, full(s), kb * 64, slice * VT_N);
-                tma_load_2d(st + 2 * VT_A_BYTES + VT_B_BYTES, bl, full(s), kb * 64, slice * VT_N);
                 if (++s == VT_STAGES) { s = 0; ph ^= 1; }
             }
         }
@@ -133,66 +145,65 @@ __global__ void __launch_bounds__(VT_THREADS, 1) k_vgru_step(const __grid_consta
             tc_commit(acc_full);
         }
     } else {
-        // 8 epilogue warps: TMEM lane quarter q = warp % 4 (hardware rule), unit half uh = 0/1 -> 16 units per thread.
+        // 16 epilogue warps: TMEM lane quarter q = warp % 4 (hardware rule), unit quarter uq = 0..3 -> 8 units per thread.
+        asm volatile("griddepcontrol.wait;" ::: "memory");
         const int q = warp & 3;
-        const int uh = (warp - 2) >> 2;
+        const int uq = (warp - 2) >> 2;
         const int row = m0 + q * 32 + lane;
         const bool valid = row < p.L;
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + uh * 16;
-        const float* bias = R.bias + slice * VT_N + uh * 16;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + uq * 8;
+        const float* bias = R.bias + slice * VT_N + uq * 8;
         // Everything that does not depend on the accumulator is fetched BEFORE waiting on the MMA, so the
         // global-load latency hides behind the TMA/MMA phase.
-        float gi[3][16], ho[16];
+        float gi[3][8], ho[8];
         if (valid && role_id != 1) {
-            const float* gp = (role_id == 0 ? R.gi + (int64_t)p.codes[row] * 1536 : R.gi + (int64_t)row * 1536) + slice * VT_N + uh * 16;
-            const float* hp = R.h_old + (int64_t)row * 512 + slice * 32 + uh * 16;
+            const float* gp = (role_id == 0 ? R.gi + (int64_t)p.codes[row] * 1536 : R.gi + (int64_t)row * 1536) + slice * VT_N + uq * 8;
+            const float* hp = R.h_old + (int64_t)row * 512 + slice * 32 + uq * 8;
 #pragma unroll
             for (int g = 0; g < 3; g++)
 #pragma unroll
-                for (int v = 0; v < 4; v++) *reinterpret_cast<float4*>(&gi[g][4 * v]) = *reinterpret_cast<const float4*>(gp + g * 32 + 4 * v);
+                for (int v = 0; v < 2; v++) *reinterpret_cast<float4*>(&gi[g][4 * v]) = *reinterpret_cast<const float4*>(gp + g * 32 + 4 * v);
 #pragma unroll
-            for (int v = 0; v < 4; v++) *reinterpret_cast<float4*>(&ho[4 * v]) = *reinterpret_cast<const float4*>(hp + 4 * v);
+            for (int v = 0; v < 2; v++) *reinterpret_cast<float4*>(&ho[4 * v]) = *reinterpret_cast<const float4*>(hp + 4 * v);
         }
         mbar_wait(acc_full, 0);
         tc_fence_after();
-#pragma unroll
-        for (int i = 0; i < 2; i++) {
-            float ar[8], az[8], an[8];
-            tmem_ld8(lane_addr + 8 * i, ar);
-            tmem_ld8(lane_addr + 32 + 8 * i, az);
-            tmem_ld8(lane_addr + 64 + 8 * i, an);
-            tmem_ld_wait();
-            if (!valid) continue;
+        float ar[8], az[8], an[8];
+        tmem_ld8(lane_addr, ar);
+        tmem_ld8(lane_addr + 32, az);
+        tmem_ld8(lane_addr + 64, an);
+        tmem_ld_wait();
+        if (valid) {
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                ar[j] += bias[8 * i + j]; az[j] += bias[32 + 8 * i + j]; an[j] += bias[64 + 8 * i + j];
+                ar[j] += bias[j]; az[j] += bias[32 + j]; an[j] += bias[64 + j];
             }
             if (role_id == 1) {
-                float* o = R.out_f32 + (int64_t)row * 1536 + slice * VT_N + uh * 16 + 8 * i;
+                float* o = R.out_f32 + (int64_t)row * 1536 + slice * VT_N + uq * 8;
                 *reinterpret_cast<float4*>(o) = make_float4(ar[0], ar[1], ar[2], ar[3]);
                 *reinterpret_cast<float4*>(o + 4) = make_float4(ar[4], ar[5], ar[6], ar[7]);
                 *reinterpret_cast<float4*>(o + 32) = make_float4(az[0], az[1], az[2], az[3]);
                 *reinterpret_cast<float4*>(o + 36) = make_float4(az[4], az[5], az[6], az[7]);
                 *reinterpret_cast<float4*>(o + 64) = make_float4(an[0], an[1], an[2], an[3]);
                 *reinterpret_cast<float4*>(o + 68) = make_float4(an[4], an[5], an[6], an[7]);
-                continue;
-            }
-            const int64_t hofs = (int64_t)row * 512 + slice * 32 + uh * 16 + 8 * i;
-            float hn[8];
-            __align__(16) __half hh[8], hl[8];
+            } else {
+                const int64_t hofs = (int64_t)row * 512 + slice * 32 + uq * 8;
+                float hn[8];
+                __align__(16) __half hh[8], hl[8];
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                float rr = sigmoid_acc(gi[0][8 * i + j] + ar[j]);
-                float zz = sigmoid_acc(gi[1][8 * i + j] + az[j]);
-                float nn = tanhf(gi[2][8 * i + j] + rr * an[j]);
-                hn[j] = (1.0f - zz) * nn + zz * ho[8 * i + j];
-                hh[j] = __float2half_rn(hn[j]);
-                hl[j] = __float2half_rn(hn[j] - __half2float(hh[j]));
+                for (int j = 0; j < 8; j++) {
+                    float rr = sigmoid_acc(gi[0][j] + ar[j]);
+                    float zz = sigmoid_acc(gi[1][j] + az[j]);
+                    float nn = tanhf(gi[2][j] + rr * an[j]);
+                    hn[j] = (1.0f - zz) * nn + zz * ho[j];
+                    hh[j] = __float2half_rn(hn[j]);
+                    hl[j] = __float2half_rn(hn[j] - __half2float(hh[j]));
+                }
+                *reinterpret_cast<float4*>(R.out_f32 + hofs) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+                *reinterpret_cast<float4*>(R.out_f32 + hofs + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
+                *reinterpret_cast<uint4*>(R.out_hi + hofs) = *reinterpret_cast<const uint4*>(hh);
+                *reinterpret_cast<uint4*>(R.out_lo + hofs) = *reinterpret_cast<const uint4*>(hl);
             }
-            *reinterpret_cast<float4*>(R.out_f32 + hofs) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-            *reinterpret_cast<float4*>(R.out_f32 + hofs + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
-            *reinterpret_cast<uint4*>(R.out_hi + hofs) = *reinterpret_cast<const uint4*>(hh);
-            *reinterpret_cast<uint4*>(R.out_lo + hofs) = *reinterpret_cast<const uint4*>(hl);
         }
     }
     tc_fence_before();
