@@ -160,7 +160,31 @@ struct Workspace {
     float* best_mean = nullptr;    // [1]
     float* coords_out = nullptr;   // [L][5][3]
     float* conf_out = nullptr;     // [L]
+    int rows2d = 0;                // rows of the 2-D track held here (L, or a strip height in halo-sharded mode)
     std::vector<void*> allocs;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// Halo-sharded fold of ONE target over `world` GPUs (strip.cu): every L x L map is split into row strips, rank g
+// owns image rows [r0, r1).  The tensors other ranks write into live in one IPC-shared window per rank with the
+// same layout everywhere; exchanges are peer stores over NVLink followed by an epoch flag, consumers spin on
+// their own flags -- no host synchronisation and no collective library on the data path.
+// ---------------------------------------------------------------------------------------------------
+enum { STRIP_FLAG_STATS = 0, STRIP_FLAG_HALO = 1, STRIP_FLAG_HEAD = 2, STRIP_NFLAGS = 3 };
+struct StripCtx {
+    int rank = 0, world = 1;
+    int L = 0, rows_per = 0, r0 = 0, r1 = 0;
+    bool attached = false, ipc = false;
+    uint8_t* win = nullptr;                    // this rank's window
+    uint8_t* peer[DMP2_MAX_RANKS] = {};        // every rank's window as mapped here (peer[rank] == win)
+    size_t win_bytes = 0;
+    size_t off_act[4] = {0, 0, 0, 0};          // xh, xl, x8lo, x8hi: [2 halo rows | rows_per | 2 halo rows][L][128]
+    size_t off_stats = 0;                      // [2 parity][world][256] double: per-rank InstanceNorm partial sums
+    size_t off_head = 0;                       // [2][L][L] float: every rank's head strip lands here
+    size_t off_flags = 0;                      // [STRIP_NFLAGS][DMP2_MAX_RANKS] uint32 epochs, indexed by source rank
+    uint32_t epoch[STRIP_NFLAGS] = {0, 0, 0};
+    unsigned int* ticket = nullptr;            // local: last-CTA detection of the push kernel
+    double* totals = nullptr;                  // local: [256] this rank's partial sums of the current map
 };
 
 struct dmp2_engine {
@@ -185,6 +209,8 @@ struct dmp2_engine {
     int vgru_mode = 0;               // 0 = tensor cores, one launch per MSA row; 1 = CUDA-core fp32 validation path; 2 = tensor cores, persistent kernel
     bool eig_no_cl16 = false;        // set when a 16-CTA cluster launch was refused
     bool attr_eig = false, attr_refine = false;   // per-engine (= per-device) cudaFuncSetAttribute done
+    StripCtx sp;                     // halo-sharded mode: window + peers (strip.cu)
+    bool strip_on = false;           // true while dmp2_fold_strip runs: the 2-D track works on rows [sp.r0, sp.r1)
     bool profile = false;            // record a CUDA-event pair around every conv launch (bench.py roofline)
     std::vector<cudaEvent_t> prof_ev;
     size_t prof_used = 0;
@@ -224,7 +250,7 @@ int run_head(dmp2_engine* e, const float* x, int L, float* head2, cudaStream_t s
 int run_head_post(dmp2_engine* e, const float* head2, int L, float* conf, float* mmat, cudaStream_t st);
 // conv_tc.cu
 int run_conv_tc(dmp2_engine* e, int blk, const __half* xh, const __half* xl, const uint8_t* x8lo, const uint8_t* x8hi, int L,
-                float* raw, int mode, cudaStream_t st);
+                int H, int y_off, int map_rows, float* raw, int mode, cudaStream_t st);
 int run_gemm_tn_test(dmp2_engine* e, const float* a, const float* b, int M, int N, int K, int mode, float* c, cudaStream_t st);
 void conv_tc_destroy(dmp2_engine* e);
 // eig.cu
@@ -236,5 +262,31 @@ int run_refine(dmp2_engine* e, float* ca, int L, int steps, cudaStream_t st);
 int run_backbone(dmp2_engine* e, const float* ca, const float* conf_logit, int L, float* out, float* conf_out, cudaStream_t st);
 int run_select(dmp2_engine* e, const float* ca, const float* conf, int L, int first, cudaStream_t st);
 
-// workspace
-int ensure_workspace(dmp2_engine* e, int L, int N);
+// strip.cu (halo-sharded mode)
+int strip_rows(int L, int world, int rank, int* r0, int* r1, int* rows_per);
+int strip_setup(dmp2_engine* e, int rank, int world, int L, unsigned char* handle_out);
+int strip_attach(dmp2_engine* e, const unsigned char* handles, void* const* ptrs);
+int strip_detach(dmp2_engine* e);
+int strip_stats_exchange(dmp2_engine* e, const float* gamma, float* norm_ss, cudaStream_t st);   // sp.totals -> all ranks -> norm_ss
+int strip_halo_push(dmp2_engine* e, cudaStream_t st);
+int strip_halo_wait(dmp2_engine* e, cudaStream_t st);
+int strip_head_gather(dmp2_engine* e, cudaStream_t st);
+// rows of the 2-D track this engine works on, and where its conv activations live
+struct Rows { int r0, R; };
+static inline Rows rows_of(const dmp2_engine* e, int L) {
+    return e->strip_on ? Rows{e->sp.r0, e->sp.r1 - e->sp.r0} : Rows{0, L};
+}
+struct ActPtrs { __half* xh; __half* xl; uint8_t* x8lo; uint8_t* x8hi; };   // first INTERIOR pixel of every copy
+static inline ActPtrs act_of(dmp2_engine* e, int L) {
+    if (!e->strip_on) return ActPtrs{e->ws.xh, e->ws.xl, e->ws.x8lo, e->ws.x8hi};
+    const int64_t skip = 2 * (int64_t)L * 128;
+    uint8_t* w = e->sp.win;
+    return ActPtrs{reinterpret_cast<__half*>(w + e->sp.off_act[0]) + skip, reinterpret_cast<__half*>(w + e->sp.off_act[1]) + skip,
+                   w + e->sp.off_act[2] + skip, w + e->sp.off_act[3] + skip};
+}
+static inline float* head_of(dmp2_engine* e) {
+    return e->strip_on ? reinterpret_cast<float*>(e->sp.win + e->sp.off_head) : e->ws.head;
+}
+
+// workspace: rows2d = rows of the 2-D track held locally (L, or the strip height in halo-sharded mode)
+int ensure_workspace(dmp2_engine* e, int L, int N, int rows2d = -1);

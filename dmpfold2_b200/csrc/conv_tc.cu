@@ -49,7 +49,9 @@ struct ConvMaps {
 
 struct TcParams {
     int gemm;            // 0 = conv (3-D activation map, taps), 1 = plain GEMM test (rows x K)
-    int L;               // conv: image side
+    int L;               // conv: image width (pixels per row)
+    int H;               // conv: output rows (== L for a whole image, the strip height for a halo-sharded fold)
+    int y_off;           // conv: row of the activation map that holds output row 0 (0, or 2 when the map starts with halo rows)
     int tiles_x;         // conv: tiles per image row
     int num_kb;          // k-blocks: conv 50, gemm K/64
     int M;               // gemm: rows
@@ -128,7 +130,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv5_tc(const __grid_consta
                 if (p.gemm) { c1 = m0; c2 = 0; }
                 else {
                     const int dy = tap / 5, dx = tap - dy * 5;
-                    c1 = x0 + dx - 2; c2 = y0 + dy - 2;
+                    c1 = x0 + dx - 2; c2 = y0 + dy - 2 + p.y_off;
                 }
                 mbar_wait(a_empty(sa), pa ^ 1);
                 mbar_expect_tx(a_full(sa), C::A_STAGE_BYTES);
@@ -231,7 +233,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv5_tc(const __grid_consta
         if (p.gemm) { valid = (m0 + r) < p.M; row = m0 + r; }
         else {
             int y = y0 + (r >> 4), x = x0 + (r & 15);
-            valid = (y < p.L) && (x < p.L);
+            valid = (y < p.H) && (x < p.L);
             row = (int64_t)y * p.L + x;
         }
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -326,7 +328,7 @@ k_conv5_tc2(const __grid_constant__ ConvMaps maps, const TcParams p) {
             for (int kb = 0; kb < p.num_kb; kb++) {
                 const int tap = kb >> 1, sub = kb & 1;
                 const int dy = tap / 5, dx = tap - dy * 5;
-                const int c1 = x0 + dx - 2, c2 = y0 + dy - 2;
+                const int c1 = x0 + dx - 2, c2 = y0 + dy - 2 + p.y_off;
                 mbar_wait(a_empty(sa), pa ^ 1);
                 const uint32_t afl = mapa_u32(a_full(sa), 0);
                 if (leader) mbar_expect_tx(a_full(sa), 2 * C::A_STAGE_BYTES);
@@ -419,7 +421,7 @@ k_conv5_tc2(const __grid_constant__ ConvMaps maps, const TcParams p) {
         mbar_wait(acc_full, 0);
         tc_fence_after();
         const int y = y0 + (r >> 4), x = x0 + (r & 15);
-        const bool valid = (y < p.L) && (x < p.L);
+        const bool valid = (y < p.H) && (x < p.L);
         const int64_t row = (int64_t)y * p.L + x;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
         for (int ch = 0; ch < 16; ch++) {
@@ -453,7 +455,7 @@ struct TcState {
     bool wmap_ok[DMP2_NBLOCKS] = {false};
     CUtensorMap amap[4];                             // a_hi, a_lo, a8_lo, a8_hi
     const void* amap_ptr = nullptr;
-    int amap_L = 0;
+    int amap_L = 0, amap_rows = 0;
     bool attr_set = false;
 };
 
@@ -531,8 +533,10 @@ int launch_cl(dmp2_engine* e, int cl, const ConvMaps& maps, const TcParams& p, i
 
 }  // namespace
 
+// xh/xl/x8lo/x8hi: activation maps of map_rows x L pixels; output row y reads map rows y + y_off - 2 .. y + y_off + 2
+// (rows outside the map read as zero), H output rows are written to raw.  Whole image: map_rows = H = L, y_off = 0.
 int run_conv_tc(dmp2_engine* e, int blk, const __half* xh, const __half* xl, const uint8_t* x8lo, const uint8_t* x8hi, int L,
-                float* raw, int mode, cudaStream_t st) {
+                int H, int y_off, int map_rows, float* raw, int mode, cudaStream_t st) {
     TcState* s;
     TRY(get_state(e, &s));
     const ResBlockW& bw = e->w.blk[blk];
@@ -543,22 +547,22 @@ int run_conv_tc(dmp2_engine* e, int blk, const __half* xh, const __half* xl, con
         TRY(weight_map(e, &s->wmap[blk][3], bw.w8_lo, 3200, 1));
         s->wmap_ok[blk] = true;
     }
-    if (s->amap_ptr != xh || s->amap_L != L) {
-        uint64_t dims[3] = {128, (uint64_t)L, (uint64_t)L};
+    if (s->amap_ptr != xh || s->amap_L != L || s->amap_rows != map_rows) {
+        uint64_t dims[3] = {128, (uint64_t)L, (uint64_t)map_rows};
         uint64_t str16[2] = {256, (uint64_t)L * 256}, str8[2] = {128, (uint64_t)L * 128};
         uint32_t box16[3] = {KCHUNK, TILE_W, TILE_H}, box8[3] = {128, TILE_W, TILE_H};
         TRY(encode(e, &s->amap[0], xh, 2, 3, dims, str16, box16));
         TRY(encode(e, &s->amap[1], xl, 2, 3, dims, str16, box16));
         TRY(encode(e, &s->amap[2], x8lo, 1, 3, dims, str8, box8));
         TRY(encode(e, &s->amap[3], x8hi, 1, 3, dims, str8, box8));
-        s->amap_ptr = xh; s->amap_L = L;
+        s->amap_ptr = xh; s->amap_L = L; s->amap_rows = map_rows;
     }
     ConvMaps maps;
     maps.a_hi = s->amap[0]; maps.a_lo = s->amap[1]; maps.a8_lo = s->amap[2]; maps.a8_hi = s->amap[3];
     maps.b_hi = s->wmap[blk][0]; maps.b_lo = s->wmap[blk][1]; maps.b8_w = s->wmap[blk][2]; maps.b8_lo = s->wmap[blk][3];
     TcParams p;
-    p.gemm = 0; p.L = L; p.tiles_x = cdiv(L, TILE_W); p.num_kb = 50; p.M = L * L; p.out = raw; p.bias = bw.bias;
-    const int grid = p.tiles_x * cdiv(L, TILE_H);
+    p.gemm = 0; p.L = L; p.H = H; p.y_off = y_off; p.tiles_x = cdiv(L, TILE_W); p.num_kb = 50; p.M = H * L; p.out = raw; p.bias = bw.bias;
+    const int grid = p.tiles_x * cdiv(H, TILE_H);
     const int cl = e->conv_cluster;
     if (mode == DMP2_CONV_TC_F16X3) return launch_cl<M_F16X3>(e, cl, maps, p, grid, st);
     if (mode == DMP2_CONV_TC_F16F8) return launch_cl<M_F16F8>(e, cl, maps, p, grid, st);
@@ -589,7 +593,7 @@ int run_gemm_tn_test(dmp2_engine* e, const float* a, const float* b, int M, int 
         if ((rc = weight_map(e, &maps.b_lo, bl, K, 2))) break;
         maps.a8_lo = maps.a_hi; maps.a8_hi = maps.a_hi; maps.b8_w = maps.b_hi; maps.b8_lo = maps.b_hi;    // unused in these modes
         TcParams p;
-        p.gemm = 1; p.L = 0; p.tiles_x = 1; p.num_kb = K / KCHUNK; p.M = M; p.out = c; p.bias = nullptr;
+        p.gemm = 1; p.L = 0; p.H = 0; p.y_off = 0; p.tiles_x = 1; p.num_kb = K / KCHUNK; p.M = M; p.out = c; p.bias = nullptr;
         int grid = cdiv(M, TILE_M);
         rc = (mode == DMP2_CONV_TC_F16X3) ? launch<M_F16X3, 1>(e, maps, p, grid, st) : launch<M_F16, 1>(e, maps, p, grid, st);
     } while (0);

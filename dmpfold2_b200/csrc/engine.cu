@@ -228,14 +228,16 @@ static int wsalloc(dmp2_engine* e, T** p, int64_t count) {
     return 0;
 }
 
-int ensure_workspace(dmp2_engine* e, int L, int N) {
+int ensure_workspace(dmp2_engine* e, int L, int N, int rows2d) {
     Workspace& ws = e->ws;
-    if (ws.L >= L && ws.N >= N) return 0;
-    L = std::max(L, ws.L);
+    if (rows2d < 0) rows2d = L;
+    // halo-sharded folds keep only their strip of the 2-D track (and the conv operand copies in the window)
+    if (ws.L >= L && ws.N >= N && ((int64_t)ws.rows2d * ws.L >= (int64_t)rows2d * L)) return 0;
+    if (rows2d == L) { L = std::max(L, ws.L); rows2d = L; }
     N = std::max(N, ws.N);
     CUDA_TRY(e, cudaDeviceSynchronize());
     free_workspace(e);
-    const int64_t P = (int64_t)L * L, Npad = (N + 3) & ~3, n = 21 * (int64_t)L, npad = (n + 63) & ~(int64_t)63;
+    const int64_t P = (int64_t)L * L, P2 = (int64_t)rows2d * L, PA = rows2d == L ? P : 1, Npad = (N + 3) & ~3, n = 21 * (int64_t)L, npad = (n + 63) & ~(int64_t)63;
     TRY(wsalloc(e, &ws.msa, (int64_t)N * L));
     TRY(wsalloc(e, &ws.msa_t, (int64_t)L * Npad));
     TRY(wsalloc(e, &ws.seqw, N));
@@ -266,13 +268,13 @@ int ensure_workspace(dmp2_engine* e, int L, int N) {
     TRY(wsalloc(e, &ws.seq_b, (int64_t)L * 512));
     TRY(wsalloc(e, &ws.mat1d_t, (int64_t)L * 512));
     TRY(wsalloc(e, &ws.dmap, P));
-    TRY(wsalloc(e, &ws.base384, P * 384));
-    TRY(wsalloc(e, &ws.raw, P * 128));
-    TRY(wsalloc(e, &ws.x, P * 128));
-    TRY(wsalloc(e, &ws.xh, P * 128));
-    TRY(wsalloc(e, &ws.xl, P * 128));
-    TRY(wsalloc(e, &ws.x8lo, P * 128));
-    TRY(wsalloc(e, &ws.x8hi, P * 128));
+    TRY(wsalloc(e, &ws.base384, P2 * 384));
+    TRY(wsalloc(e, &ws.raw, P2 * 128));
+    TRY(wsalloc(e, &ws.x, P2 * 128));
+    TRY(wsalloc(e, &ws.xh, PA * 128));
+    TRY(wsalloc(e, &ws.xl, PA * 128));
+    TRY(wsalloc(e, &ws.x8lo, PA * 128));
+    TRY(wsalloc(e, &ws.x8hi, PA * 128));
     TRY(wsalloc(e, &ws.stat_part, (int64_t)e->num_sms * 4 * 256));
     TRY(wsalloc(e, &ws.norm_ss, 256));
     TRY(wsalloc(e, &ws.ticket, 64));
@@ -292,6 +294,7 @@ int ensure_workspace(dmp2_engine* e, int L, int N) {
     TRY(wsalloc(e, &ws.conf_out, L));
     ws.L = L;
     ws.N = N;
+    ws.rows2d = rows2d;
     return 0;
 }
 
@@ -308,8 +311,9 @@ static int one_pass(dmp2_engine* e, int L, cudaStream_t st) {
     Workspace& ws = e->ws;
     TRY(run_stem_update(e, ws.dmap, L, st));
     for (int k = 0; k < DMP2_NBLOCKS; k++) TRY(run_resblock(e, k, L, st));
-    TRY(run_head(e, ws.x, L, ws.head, st));
-    TRY(run_head_post(e, ws.head, L, ws.conf, ws.mmat, st));
+    float* head = head_of(e);                  // halo-sharded: the window, where the peers' rows land too
+    TRY(run_head(e, ws.x, L, head, st));
+    TRY(run_head_post(e, head, L, ws.conf, ws.mmat, st));
     TRY(run_eig_top8(e, ws.mmat, L, ws.eig_val, ws.mds, nullptr, st));
     TRY(run_coord_head(e, ws.mat1d_t, ws.mds, L, ws.ca, st));
     return 0;
@@ -423,6 +427,7 @@ void dmp2_destroy(dmp2_engine* e) {
     conv_tc_destroy(e);
     vgru_tc_destroy(e);
     vgru_persist_destroy(e);
+    strip_detach(e);
     free_workspace(e);
     for (void* p : e->weight_allocs) cudaFree(p);
     if (e->ev_ok) for (int i = 0; i < 16; i++) cudaEventDestroy(e->ev[i]);
@@ -495,13 +500,71 @@ int dmp2_fold(dmp2_engine* e, const uint8_t* msa_dev, int N, int L, const float*
     return fold_impl(e, msa_dev, N, L, tmpl_ca_dev, iterations, minsteps, coords_out_dev, conf_out_dev, (cudaStream_t)stream, false);
 }
 
+// halo-sharded mode: same contract as dmp2_fold, but COLLECTIVE -- every rank of the strip group calls it with the
+// same arguments; the 2-D track runs on this rank's rows, everything else is replicated, all ranks get the result.
+static int strip_ready(dmp2_engine* e, int L) {
+    if (!e->sp.attached || e->sp.L != L)
+        return e->fail(DMP2_ERR_BAD_ARG, "fold_strip: call dmp2_strip_setup + dmp2_strip_attach for this L on every rank first");
+    if (e->conv_mode == DMP2_CONV_FFMA) return e->fail(DMP2_ERR_UNSUPPORTED, "fold_strip: the CUDA-core validation conv has no halo-sharded form");
+    return 0;
+}
+
+int dmp2_fold_strip(dmp2_engine* e, const uint8_t* msa_dev, int N, int L, const float* tmpl_ca_dev, int iterations, int minsteps,
+                    float* coords_out_dev, float* conf_out_dev, void* stream) {
+    if (!e) return DMP2_ERR_BAD_ARG;
+    TRY(check_device(e));
+    if (L < 8 || N < 1) return e->fail(DMP2_ERR_BAD_ARG, "fold_strip: need L >= 8 and N >= 1");
+    TRY(strip_ready(e, L));
+    TRY(ensure_workspace(e, L, N, e->sp.r1 - e->sp.r0));
+    e->strip_on = true;
+    int rc = fold_impl(e, msa_dev, N, L, tmpl_ca_dev, iterations, minsteps, coords_out_dev, conf_out_dev, (cudaStream_t)stream, false);
+    e->strip_on = false;
+    return rc;
+}
+
+static int fold_host_impl(dmp2_engine* e, const uint8_t* msa_host, int N, int L, const float* tmpl_ca_host, int iterations,
+                          int minsteps, float* coords_out_host, float* conf_out_host, bool strip);
+
+int dmp2_fold_strip_host(dmp2_engine* e, const uint8_t* msa_host, int N, int L, const float* tmpl_ca_host, int iterations,
+                         int minsteps, float* coords_out_host, float* conf_out_host) {
+    return fold_host_impl(e, msa_host, N, L, tmpl_ca_host, iterations, minsteps, coords_out_host, conf_out_host, true);
+}
+
+int dmp2_strip_rows(int L, int world, int rank, int* r0, int* r1) { return strip_rows(L, world, rank, r0, r1, nullptr); }
+
+int dmp2_strip_setup(dmp2_engine* e, int rank, int world, int L, int reserve_N, unsigned char* handle_out, void** window_out) {
+    if (!e) return DMP2_ERR_BAD_ARG;
+    TRY(strip_setup(e, rank, world, L, handle_out));
+    if (reserve_N > 0) TRY(ensure_workspace(e, L, reserve_N, e->sp.r1 - e->sp.r0));   // no allocation (= device sync) inside the folds
+    if (window_out) *window_out = e->sp.win;
+    return 0;
+}
+int dmp2_strip_attach(dmp2_engine* e, const unsigned char* handles) {
+    if (!e) return DMP2_ERR_BAD_ARG;
+    return strip_attach(e, handles, nullptr);
+}
+int dmp2_strip_attach_local(dmp2_engine* e, void* const* windows) {
+    if (!e) return DMP2_ERR_BAD_ARG;
+    return strip_attach(e, nullptr, windows);
+}
+int dmp2_strip_detach(dmp2_engine* e) {
+    if (!e) return DMP2_ERR_BAD_ARG;
+    return strip_detach(e);
+}
+
 int dmp2_fold_host(dmp2_engine* e, const uint8_t* msa_host, int N, int L, const float* tmpl_ca_host, int iterations,
                    int minsteps, float* coords_out_host, float* conf_out_host) {
+    return fold_host_impl(e, msa_host, N, L, tmpl_ca_host, iterations, minsteps, coords_out_host, conf_out_host, false);
+}
+
+static int fold_host_impl(dmp2_engine* e, const uint8_t* msa_host, int N, int L, const float* tmpl_ca_host, int iterations,
+                          int minsteps, float* coords_out_host, float* conf_out_host, bool strip) {
     if (!e) return DMP2_ERR_BAD_ARG;
     if (!msa_host || !coords_out_host || !conf_out_host) return e->fail(DMP2_ERR_BAD_ARG, "fold_host: null pointer");
     if (L < 8 || N < 1) return e->fail(DMP2_ERR_BAD_ARG, "fold_host: need L >= 8 and N >= 1");
     TRY(check_device(e));
-    TRY(ensure_workspace(e, L, N));
+    if (strip) TRY(strip_ready(e, L));
+    TRY(ensure_workspace(e, L, N, strip ? e->sp.r1 - e->sp.r0 : -1));
     Workspace& ws = e->ws;
     cudaStream_t st = 0;
     CUDA_TRY(e, cudaMemcpyAsync(ws.msa, msa_host, (size_t)N * L, cudaMemcpyHostToDevice, st));
@@ -510,7 +573,10 @@ int dmp2_fold_host(dmp2_engine* e, const uint8_t* msa_host, int N, int L, const 
         tmpl = ws.best_ca;       // staged here; consumed by run_dmap before best_ca is first written
         CUDA_TRY(e, cudaMemcpyAsync(tmpl, tmpl_ca_host, (size_t)3 * L * sizeof(float), cudaMemcpyHostToDevice, st));
     }
-    TRY(fold_impl(e, ws.msa, N, L, tmpl, iterations, minsteps, ws.coords_out, ws.conf_out, st, true));
+    e->strip_on = strip;
+    int rc = fold_impl(e, ws.msa, N, L, tmpl, iterations, minsteps, ws.coords_out, ws.conf_out, st, true);
+    e->strip_on = false;
+    if (rc != 0) return rc;
     CUDA_TRY(e, cudaMemcpyAsync(coords_out_host, ws.coords_out, (size_t)15 * L * sizeof(float), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(e, cudaMemcpyAsync(conf_out_host, ws.conf_out, (size_t)L * sizeof(float), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(e, cudaStreamSynchronize(st));
@@ -552,7 +618,7 @@ int dmp2_conv5_maxout(dmp2_engine* e, int block, const float* x_nhwc_dev, int L,
     if (block < 1 || block > DMP2_NBLOCKS) return e->fail(DMP2_ERR_BAD_ARG, "conv5_maxout: block must be 1..16");
     if (e->conv_mode == DMP2_CONV_FFMA) return run_conv_ffma(e, block - 1, x_nhwc_dev, L, out_nhwc_dev, st);
     TRY(run_split_half(e, x_nhwc_dev, (int64_t)L * L * 128, e->ws.xh, e->ws.xl, e->ws.x8lo, e->ws.x8hi, st));
-    return run_conv_tc(e, block - 1, e->ws.xh, e->ws.xl, e->ws.x8lo, e->ws.x8hi, L, out_nhwc_dev, e->conv_mode, st);
+    return run_conv_tc(e, block - 1, e->ws.xh, e->ws.xl, e->ws.x8lo, e->ws.x8hi, L, L, 0, L, out_nhwc_dev, e->conv_mode, st);
 }
 
 int dmp2_resblock(dmp2_engine* e, int block, const float* x_nhwc_dev, int L, float* out_nhwc_dev, void* stream) {

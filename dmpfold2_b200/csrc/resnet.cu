@@ -22,7 +22,9 @@ struct StemLoad {
     const float* m1t;            // [L][512] hgru output (time-major)
     const float* feat;           // [L*L][444]
     int L;
+    int m0;                      // first pixel of this engine's rows (0 unless halo-sharded)
     __device__ float4 operator()(int m, int k) const {
+        m += m0;
         if (k < 512) {
             int i = m / L, j = m - i * L;
             float4 a = *reinterpret_cast<const float4*>(m1t + (int64_t)i * 512 + k);
@@ -34,7 +36,8 @@ struct StemLoad {
 };
 
 int run_stem_base(dmp2_engine* e, const float* mat1d_t, const float* feat444, int L, cudaStream_t st) {
-    sgemm_launch<8>(L * L, 384, DMP2_STEM_K, StemLoad{mat1d_t, feat444, L}, LoadRowMajorK{e->w.stem_w, DMP2_STEM_K},
+    const Rows rw = rows_of(e, L);
+    sgemm_launch<8>(rw.R * L, 384, DMP2_STEM_K, StemLoad{mat1d_t, feat444, L, rw.r0 * L}, LoadRowMajorK{e->w.stem_w, DMP2_STEM_K},
                     StoreRowMajor{e->ws.base384, 384, e->w.stem_b, 1.0f}, st);
     POST_LAUNCH(e, "sgemm<stem>");
     return 0;
@@ -59,7 +62,8 @@ __global__ void __launch_bounds__(256) k_stem_update(const float* __restrict__ b
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(512) k_in_stats(const float* __restrict__ raw, int64_t npix, const float* __restrict__ gamma,
                                                    double* __restrict__ part, unsigned int* __restrict__ ticket,
-                                                   float* __restrict__ norm /* [mean 128 | gamma*rstd 128] */) {
+                                                   float* __restrict__ norm /* [mean 128 | gamma*rstd 128] */,
+                                                   double* __restrict__ totals /* halo-sharded: [sum 128 | sumsq 128] of these rows, norm unused */) {
     // 32 lanes x float4 cover one pixel's 128 channels; 16 pixel groups per CTA; 4 loads in flight per thread
     const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
     double s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
@@ -125,6 +129,11 @@ __global__ void __launch_bounds__(512) k_in_stats(const float* __restrict__ raw,
         sh[0][threadIdx.x] = t;
     }
     __syncthreads();
+    if (totals) {                                      // the cross-rank fold finishes the statistics (strip.cu)
+        if (threadIdx.x < 256) totals[threadIdx.x] = sh[0][threadIdx.x];
+        if (threadIdx.x == 0) *ticket = 0;
+        return;
+    }
     if (threadIdx.x < 128) {
         const int c = threadIdx.x;
         double mean = sh[0][c] / (double)npix;
@@ -207,27 +216,32 @@ int run_split_half(dmp2_engine* e, const float* x, int64_t n, __half* hi, __half
 
 int run_stem_update(dmp2_engine* e, const float* dmap, int L, cudaStream_t st) {
     Workspace& ws = e->ws;
-    const int64_t npix = (int64_t)L * L;
+    const Rows rw = rows_of(e, L);
+    const int64_t npix = (int64_t)rw.R * L;
     int grid = (int)std::min<int64_t>(cdiv64(npix, 2), (int64_t)e->num_sms * 8);
-    k_stem_update<<<grid, 256, 0, st>>>(ws.base384, e->w.stem_wd, dmap, npix, ws.raw);
+    k_stem_update<<<grid, 256, 0, st>>>(ws.base384, e->w.stem_wd, dmap + (int64_t)rw.r0 * L, npix, ws.raw);
     POST_LAUNCH(e, "k_stem_update");
     return run_norm_gate(e, -1, ws.raw, ws.x, L, true, st);
 }
 
 int run_norm_gate(dmp2_engine* e, int blk, const float* raw, float* x, int L, bool stem, cudaStream_t st) {
     Workspace& ws = e->ws;
-    const int64_t npix = (int64_t)L * L;
+    const Rows rw = rows_of(e, L);
+    const int64_t npix = (int64_t)rw.R * L;
     const float* gamma = stem ? e->w.stem_gamma : e->w.blk[blk].gamma;
     const float* beta = stem ? e->w.stem_beta : e->w.blk[blk].beta;
     int sgrid = (int)std::min<int64_t>(cdiv64(npix, 64), (int64_t)e->num_sms * 2);
-    k_in_stats<<<sgrid, 512, 0, st>>>(raw, npix, gamma, ws.stat_part, ws.ticket, ws.norm_ss);
+    k_in_stats<<<sgrid, 512, 0, st>>>(raw, npix, gamma, ws.stat_part, ws.ticket, ws.norm_ss, e->strip_on ? e->sp.totals : nullptr);
     POST_LAUNCH(e, "k_in_stats");
+    if (e->strip_on) TRY(strip_stats_exchange(e, gamma, ws.norm_ss, st));      // statistics are over ALL rows of the map
+    const ActPtrs act = act_of(e, L);
     int agrid = (int)std::min<int64_t>(cdiv64(npix, 8), (int64_t)e->num_sms * 8);
     k_norm_gate<<<agrid, 256, 0, st>>>(raw, ws.norm_ss, beta, stem ? nullptr : e->w.blk[blk].gate_c,
                                        stem ? nullptr : e->w.blk[blk].sse_w, stem ? 0.f : e->w.blk[blk].sse_b, stem ? 1 : 0,
-                                       npix, x, ws.xh, ws.xl, ws.x8lo, ws.x8hi, e->conv_mode == DMP2_CONV_TC_F16X3 ? 1 : 0,
+                                       npix, x, act.xh, act.xl, act.x8lo, act.x8hi, e->conv_mode == DMP2_CONV_TC_F16X3 ? 1 : 0,
                                        e->conv_mode == DMP2_CONV_TC_F16F8 ? 1 : 0);
     POST_LAUNCH(e, "k_norm_gate");
+    if (e->strip_on && blk != DMP2_NBLOCKS - 1) TRY(strip_halo_push(e, st));   // the next conv reads 2 rows of each neighbour
     return 0;
 }
 
@@ -267,8 +281,15 @@ int run_resblock(dmp2_engine* e, int blk, int L, cudaStream_t st) {
     Workspace& ws = e->ws;
     const bool prof = e->profile && e->prof_used + 2 <= e->prof_ev.size();
     if (prof) cudaEventRecord(e->prof_ev[e->prof_used], st);
-    if (e->conv_mode == DMP2_CONV_FFMA) TRY(run_conv_ffma(e, blk, ws.x, L, ws.raw, st));
-    else TRY(run_conv_tc(e, blk, ws.xh, ws.xl, ws.x8lo, ws.x8hi, L, ws.raw, e->conv_mode, st));
+    if (e->strip_on) {
+        // strip of R rows; the activation copies carry 2 halo rows on each side, filled by the neighbours
+        const Rows rw = rows_of(e, L);
+        const StripCtx& sp = e->sp;
+        TRY(strip_halo_wait(e, st));
+        TRY(run_conv_tc(e, blk, reinterpret_cast<const __half*>(sp.win + sp.off_act[0]), reinterpret_cast<const __half*>(sp.win + sp.off_act[1]),
+                        sp.win + sp.off_act[2], sp.win + sp.off_act[3], L, rw.R, 2, rw.R + 4, ws.raw, e->conv_mode, st));
+    } else if (e->conv_mode == DMP2_CONV_FFMA) TRY(run_conv_ffma(e, blk, ws.x, L, ws.raw, st));
+    else TRY(run_conv_tc(e, blk, ws.xh, ws.xl, ws.x8lo, ws.x8hi, L, L, 0, L, ws.raw, e->conv_mode, st));
     if (prof) { cudaEventRecord(e->prof_ev[e->prof_used + 1], st); e->prof_used += 2; }
     return run_norm_gate(e, blk, ws.raw, ws.x, L, false, st);
 }
@@ -278,7 +299,7 @@ int run_resblock(dmp2_engine* e, int blk, int L, cudaStream_t st) {
 // M[i][j] = 0.5 * (dm[0][j]^2 + dm[i][0]^2 - dm[i][j]^2)                               (network.py:237-246)
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_head(const float* __restrict__ x, const float* __restrict__ w, float b0, float b1,
-                                              int64_t npix, float* __restrict__ head) {
+                                              int64_t npix, float* __restrict__ head0, float* __restrict__ head1) {
     const int lane = threadIdx.x & 31;
     const float4 w0 = *reinterpret_cast<const float4*>(w + lane * 4);
     const float4 w1 = *reinterpret_cast<const float4*>(w + 128 + lane * 4);
@@ -292,7 +313,7 @@ __global__ void __launch_bounds__(256) k_head(const float* __restrict__ x, const
             d0 += __shfl_xor_sync(0xffffffffu, d0, s);
             d1 += __shfl_xor_sync(0xffffffffu, d1, s);
         }
-        if (lane == 0) { head[p] = d0 + b0; head[npix + p] = d1 + b1; }
+        if (lane == 0) { head0[p] = d0 + b0; head1[p] = d1 + b1; }
     }
 }
 
@@ -327,10 +348,13 @@ __global__ void __launch_bounds__(256) k_head_post(const float* __restrict__ hea
 }
 
 int run_head(dmp2_engine* e, const float* x, int L, float* head2, cudaStream_t st) {
-    const int64_t npix = (int64_t)L * L;
+    // x: this engine's rows of the residual stream; head2: the whole (2, L, L) map (other rows come from the peers)
+    const Rows rw = rows_of(e, L);
+    const int64_t npix = (int64_t)rw.R * L, first = (int64_t)rw.r0 * L;
     int grid = (int)std::min<int64_t>(cdiv64(npix, 8), (int64_t)e->num_sms * 8);
-    k_head<<<grid, 256, 0, st>>>(x, e->w.head_w, e->w.head_b[0], e->w.head_b[1], npix, head2);
+    k_head<<<grid, 256, 0, st>>>(x, e->w.head_w, e->w.head_b[0], e->w.head_b[1], npix, head2 + first, head2 + (int64_t)L * L + first);
     POST_LAUNCH(e, "k_head");
+    if (e->strip_on) TRY(strip_head_gather(e, st));
     return 0;
 }
 int run_head_post(dmp2_engine* e, const float* head2, int L, float* conf, float* mmat, cudaStream_t st) {

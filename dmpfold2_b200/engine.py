@@ -34,6 +34,13 @@ _SIGS = {
     'dmp2_conv_profile': (_i, [_vp, C.POINTER(_i), C.POINTER(C.c_float)]),
     'dmp2_fold': (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp]),
     'dmp2_fold_host': (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _vp]),
+    'dmp2_strip_rows': (_i, [_i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
+    'dmp2_strip_setup': (_i, [_vp, _i, _i, _i, _i, _vp, C.POINTER(_vp)]),
+    'dmp2_strip_attach': (_i, [_vp, _vp]),
+    'dmp2_strip_attach_local': (_i, [_vp, C.POINTER(_vp)]),
+    'dmp2_strip_detach': (_i, [_vp]),
+    'dmp2_fold_strip': (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp]),
+    'dmp2_fold_strip_host': (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _vp]),
     'dmp2_reweight': (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     'dmp2_dca': (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     'dmp2_vgru': (_i, [_vp, _vp, _i, _i, _vp, _vp]),
@@ -68,6 +75,19 @@ def load_library() -> C.CDLL:
 
 class Dmp2Error(RuntimeError):
     pass
+
+
+IPC_HANDLE_BYTES = 64
+MAX_RANKS = 8
+
+
+def strip_rows(l: int, world: int, rank: int) -> Tuple[int, int]:
+    """Rows [r0, r1) of every L x L map owned by `rank` in a halo-sharded fold (dmp2_strip_rows; host arithmetic,
+    works without a GPU).  Raises ValueError when L is too short for `world` strips."""
+    r0, r1 = C.c_int(), C.c_int()
+    if load_library().dmp2_strip_rows(int(l), int(world), int(rank), C.byref(r0), C.byref(r1)) != 0:
+        raise ValueError(f'cannot split L={l} into {world} row strips (rank {rank}): every strip needs at least 2 rows')
+    return r0.value, r1.value
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -180,6 +200,60 @@ class Engine:
                                      None if tm is None else tm.ctypes.data_as(C.c_void_p), int(iterations), int(minsteps),
                                      coords.ctypes.data_as(C.c_void_p), conf.ctypes.data_as(C.c_void_p))
         self._check(st, 'dmp2_fold_host')
+        return coords, conf
+
+    # ---- halo-sharded fold of one target over several GPUs ------------------------------------------
+    def strip_setup(self, rank: int, world: int, l: int, reserve_n: int = 0) -> Tuple[bytes, int]:
+        """Allocate this rank's exchange window for targets of length l (and the workspace for up to reserve_n
+        alignment rows) -> (CUDA IPC handle, device address)."""
+        handle = (C.c_ubyte * IPC_HANDLE_BYTES)()
+        win = C.c_void_p()
+        self._check(self.lib.dmp2_strip_setup(self.h, int(rank), int(world), int(l), int(reserve_n), C.cast(handle, C.c_void_p),
+                                              C.byref(win)), 'dmp2_strip_setup')
+        return bytes(handle), int(win.value)
+
+    def strip_attach(self, handles) -> None:
+        """handles: every rank's IPC handle in rank order (ranks in separate processes)."""
+        blob = b''.join(handles)
+        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        self._check(self.lib.dmp2_strip_attach(self.h, C.cast(buf, C.c_void_p)), 'dmp2_strip_attach')
+
+    def strip_attach_local(self, windows) -> None:
+        """windows: every rank's window address in rank order (all ranks are engines of THIS process)."""
+        arr = (C.c_void_p * len(windows))(*[C.c_void_p(w) for w in windows])
+        self._check(self.lib.dmp2_strip_attach_local(self.h, arr), 'dmp2_strip_attach_local')
+
+    def strip_detach(self) -> None:
+        self._check(self.lib.dmp2_strip_detach(self.h), 'dmp2_strip_detach')
+
+    def fold_strip(self, msa: torch.Tensor, template_ca: Optional[torch.Tensor] = None, iterations: int = 10,
+                   minsteps: int = 100, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Collective form of fold(): every rank of the strip group calls it with the same arguments.
+        out = preallocated (coords (L,5,3), confs (L,)) float32 tensors on the engine's device, optional."""
+        msa = self._dev(msa, torch.uint8)
+        n, l = msa.shape
+        tm = None if template_ca is None else self._dev(template_ca, torch.float32)
+        if tm is not None and tuple(tm.shape) != (l, 3):
+            raise ValueError(f'template has {tm.shape[0]} CA atoms, alignment has {l} columns')
+        coords, conf = out if out is not None else (self._empty(l, 5, 3), self._empty(l))
+        with torch.cuda.device(self.device):
+            st = self.lib.dmp2_fold_strip(self.h, _ptr(msa), n, l, _ptr(tm), int(iterations), int(minsteps), _ptr(coords),
+                                          _ptr(conf), self._stream())
+        self._check(st, 'dmp2_fold_strip')
+        return coords, conf
+
+    def fold_strip_host(self, msa: np.ndarray, template_ca: Optional[np.ndarray] = None, iterations: int = 10,
+                        minsteps: int = 100) -> Tuple[np.ndarray, np.ndarray]:
+        """Collective form of fold_host()."""
+        msa = np.ascontiguousarray(msa, dtype=np.uint8)
+        n, l = msa.shape
+        tm = None if template_ca is None else np.ascontiguousarray(template_ca, dtype=np.float32)
+        coords = np.empty((l, 5, 3), dtype=np.float32)
+        conf = np.empty((l,), dtype=np.float32)
+        st = self.lib.dmp2_fold_strip_host(self.h, msa.ctypes.data_as(C.c_void_p), n, l,
+                                           None if tm is None else tm.ctypes.data_as(C.c_void_p), int(iterations), int(minsteps),
+                                           coords.ctypes.data_as(C.c_void_p), conf.ctypes.data_as(C.c_void_p))
+        self._check(st, 'dmp2_fold_strip_host')
         return coords, conf
 
     # ---- stage entry points (parity tests) -------------------------------------------------------

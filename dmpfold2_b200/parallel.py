@@ -1,6 +1,12 @@
-"""Multi-GPU plumbing: independent alignments are sharded one-per-GPU, one process per GPU, with NO data-path
-collective.  torch.distributed (NCCL on GPUs, gloo in the CPU tests) is used only to
-agree on the shard, to gather the small per-target results and to take the max-over-ranks of a device time.
+"""Multi-GPU plumbing.
+
+Independent alignments are sharded one-per-GPU, one process per GPU, with NO data-path collective (SURVEY.md
+section 8e): torch.distributed (NCCL on GPUs, gloo in the CPU tests) is used only to agree on the shard, to gather the
+small per-target results and to take the max-over-ranks of a device time.
+
+One LONG target can instead be halo-sharded over the ranks (BASELINE.json configs[4]): `StripGroup` exchanges the
+CUDA IPC handles of the engines' windows once through torch.distributed; after that the ranks talk through peer
+stores + flags inside the kernels' stream (csrc/strip.cu) and torch.distributed is not involved in a fold.
 """
 from __future__ import annotations
 
@@ -53,3 +59,55 @@ def fold_many(targets: Sequence, fold_fn: Callable[[object], object], gather: bo
     for p in parts:
         merged.update(p)
     return [merged[t] for t in range(len(targets))]
+
+
+def exchange_handles(handle: bytes) -> List[bytes]:
+    """All-gather one small bytes object per rank, in rank order (works on gloo and NCCL groups)."""
+    rank, ws = world()
+    if ws == 1:
+        return [handle]
+    parts: List[Optional[bytes]] = [None] * ws
+    dist.all_gather_object(parts, handle)
+    return list(parts)
+
+
+class StripGroup:
+    """The ranks of the current process group folding ONE target together, every L x L map split in row strips.
+
+    Every rank constructs it with its own engine and calls fold() with the same alignment; every rank gets the full
+    (L,5,3) coordinates and (L,) confidences back (the parts of the path that are not sharded are replicated).
+    The windows are sized for one alignment length; fold() re-creates them (a collective step) when L changes.
+    """
+
+    def __init__(self, engine):
+        self.engine = engine
+        self.rank, self.world = world()
+        self.l = None
+
+    def _setup(self, l: int, n: int = 0):
+        if self.l == l:
+            return
+        self.close()
+        handle, _ = self.engine.strip_setup(self.rank, self.world, l, n)
+        self.engine.strip_attach(exchange_handles(handle))
+        if self.world > 1:
+            dist.barrier()            # nobody starts pushing before every rank has mapped every window
+        self.l = l
+
+    def fold(self, msa, template_ca=None, iterations: int = 10, minsteps: int = 100):
+        self._setup(int(msa.shape[1]), int(msa.shape[0]))
+        return self.engine.fold_strip(msa, template_ca, iterations, minsteps)
+
+    def fold_host(self, msa, template_ca=None, iterations: int = 10, minsteps: int = 100):
+        self._setup(int(msa.shape[1]), int(msa.shape[0]))
+        return self.engine.fold_strip_host(msa, template_ca, iterations, minsteps)
+
+    def close(self):
+        if self.l is not None:
+            torch.cuda.synchronize(self.engine.device)
+            if self.world > 1:
+                dist.barrier()        # every rank has finished using its peers' windows
+            self.engine.strip_detach()
+            if self.world > 1:
+                dist.barrier()
+            self.l = None

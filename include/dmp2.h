@@ -29,6 +29,9 @@ extern "C" {
 
 typedef struct dmp2_engine dmp2_engine;
 
+#define DMP2_MAX_RANKS 8          /* GPUs one halo-sharded fold can span (one NVSwitch box) */
+#define DMP2_IPC_HANDLE_BYTES 64  /* sizeof(cudaIpcMemHandle_t) */
+
 typedef enum {
     DMP2_OK = 0,
     DMP2_ERR_BAD_ARG = -1,        /* NULL pointer, L < 8, N < 1, negative counts ...            */
@@ -88,6 +91,35 @@ int dmp2_fold(dmp2_engine* e, const uint8_t* msa_dev, int N, int L, const float*
  * synchronises.  This is the call timed as the end-to-end number. */
 int dmp2_fold_host(dmp2_engine* e, const uint8_t* msa_host, int N, int L, const float* tmpl_ca_host, int iterations,
                    int minsteps, float* coords_out_host, float* conf_out_host);
+
+/* ---- halo-sharded fold of ONE target over several GPUs (BASELINE.json configs[4]) -------------------
+ * The reference has no multi-GPU path (predict.py:74-158 is single-device); this is the form its
+ * network(...) call (predict.py:151) takes when the L x L pair maps are split into row strips over `world`
+ * GPUs, one process (or one engine) per GPU.  Rank g owns rows [r0, r1) of every map of the 2-D track
+ * (network.py:229-246); conv halo rows, InstanceNorm sums and the head rows move between the ranks' windows
+ * by peer stores over NVLink + epoch flags, with no host synchronisation.  The 1-D track, the MSA features,
+ * the eigen step, the coordinate GRU and the minimiser are replicated, so every rank returns the full result.
+ *
+ *   dmp2_strip_rows    pure host arithmetic: the rows of `rank` (multiples of 8; fails if the last rank would
+ *                      own fewer than 2 rows)
+ *   dmp2_strip_setup   allocates this rank's exchange window for targets of length L (and, if reserve_N > 0, the
+ *                      workspace for alignments of up to reserve_N rows, so that the folds allocate nothing);
+ *                      writes the window's CUDA IPC handle (64 bytes) and/or its device address
+ *   dmp2_strip_attach  maps every rank's window: `handles` = world x 64 bytes in rank order, gathered by the
+ *                      caller (e.g. torch.distributed.all_gather_object).  Ranks in separate processes.
+ *   dmp2_strip_attach_local   same for ranks living in ONE process: `windows` = world device addresses
+ *   dmp2_strip_detach  unmaps and frees; call on every rank (then barrier) before a new setup
+ *   dmp2_fold_strip / dmp2_fold_strip_host   like dmp2_fold / dmp2_fold_host, but COLLECTIVE: every rank
+ *                      calls with identical arguments.  L must equal the L given to dmp2_strip_setup. */
+int dmp2_strip_rows(int L, int world, int rank, int* r0, int* r1);
+int dmp2_strip_setup(dmp2_engine* e, int rank, int world, int L, int reserve_N, unsigned char* ipc_handle_out, void** window_out);
+int dmp2_strip_attach(dmp2_engine* e, const unsigned char* handles);
+int dmp2_strip_attach_local(dmp2_engine* e, void* const* windows);
+int dmp2_strip_detach(dmp2_engine* e);
+int dmp2_fold_strip(dmp2_engine* e, const uint8_t* msa_dev, int N, int L, const float* tmpl_ca_dev, int iterations,
+                    int minsteps, float* coords_out_dev, float* conf_out_dev, void* stream);
+int dmp2_fold_strip_host(dmp2_engine* e, const uint8_t* msa_host, int N, int L, const float* tmpl_ca_host, int iterations,
+                         int minsteps, float* coords_out_host, float* conf_out_host);
 
 /* ---- stage entry points (teacher-forced parity tests; all device pointers, async on `stream`) ------ */
 
