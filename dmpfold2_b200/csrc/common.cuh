@@ -170,7 +170,7 @@ struct Workspace {
 // same layout everywhere; exchanges are peer stores over NVLink followed by an epoch flag, consumers spin on
 // their own flags -- no host synchronisation and no collective library on the data path.
 // ---------------------------------------------------------------------------------------------------
-enum { STRIP_FLAG_STATS = 0, STRIP_FLAG_HALO = 1, STRIP_FLAG_HEAD = 2, STRIP_NFLAGS = 3 };
+enum { STRIP_FLAG_STATS = 0, STRIP_FLAG_HALO = 1, STRIP_FLAG_HEAD = 2, STRIP_FLAG_VGRU = 3, STRIP_FLAG_X3 = 4, STRIP_NFLAGS = 5 };
 struct StripCtx {
     int rank = 0, world = 1;
     int L = 0, rows_per = 0, r0 = 0, r1 = 0;
@@ -181,9 +181,11 @@ struct StripCtx {
     size_t off_act[4] = {0, 0, 0, 0};          // xh, xl, x8lo, x8hi: [2 halo rows | rows_per | 2 halo rows][L][128]
     size_t off_stats = 0;                      // [2 parity][world][256] double: per-rank InstanceNorm partial sums
     size_t off_head = 0;                       // [2][L][L] float: every rank's head strip lands here
+    size_t off_x3 = 0;                         // [L][L] float: DCA contact norms (APC needs every row's sums)
+    size_t off_vlast = 0;                      // [L][512] float: vgru output, every rank computes a range of columns
     size_t off_flags = 0;                      // [STRIP_NFLAGS][DMP2_MAX_RANKS] uint32 epochs, indexed by source rank
-    uint32_t epoch[STRIP_NFLAGS] = {0, 0, 0};
-    unsigned int* ticket = nullptr;            // local: last-CTA detection of the push kernel
+    uint32_t epoch[STRIP_NFLAGS] = {0, 0, 0, 0, 0};
+    unsigned int* ticket = nullptr;            // local: last-CTA detection of the push kernel ([0] main stream, [1] side stream)
     double* totals = nullptr;                  // local: [256] this rank's partial sums of the current map
 };
 
@@ -208,7 +210,7 @@ struct dmp2_engine {
     int conv_cluster = 2;            // CTAs per cluster sharing the conv weight stream by TMA multicast (1 = off)
     int vgru_mode = 0;               // 0 = tensor cores, one launch per MSA row; 1 = CUDA-core fp32 validation path; 2 = tensor cores, persistent kernel
     bool eig_no_cl16 = false;        // set when a 16-CTA cluster launch was refused
-    bool attr_eig = false, attr_refine = false;   // per-engine (= per-device) cudaFuncSetAttribute done
+    bool attr_eig = false, attr_refine = false, attr_eig_grid = false;   // per-engine (= per-device) cudaFuncSetAttribute done
     StripCtx sp;                     // halo-sharded mode: window + peers (strip.cu)
     bool strip_on = false;           // true while dmp2_fold_strip runs: the 2-D track works on rows [sp.r0, sp.r1)
     bool profile = false;            // record a CUDA-event pair around every conv launch (bench.py roofline)
@@ -233,7 +235,7 @@ int run_feat_import(dmp2_engine* e, const float* feat442, int L, float* feat444,
 // gru.cu
 int run_vgru(dmp2_engine* e, const uint8_t* msa, int N, int L, float* out, cudaStream_t st);
 int run_vgru_ffma(dmp2_engine* e, const uint8_t* msa, int N, int L, float* out, cudaStream_t st);
-int run_vgru_tc(dmp2_engine* e, const uint8_t* msa, int N, int L, float* out, cudaStream_t st);
+int run_vgru_tc(dmp2_engine* e, const uint8_t* msa, int N, int L, float* out, cudaStream_t st, int ld = 0);   // ld: row stride of msa (0 = L)
 void vgru_tc_destroy(dmp2_engine* e);
 int run_vgru_persist(dmp2_engine* e, const uint8_t* msa, int N, int L, float* out, cudaStream_t st);
 void vgru_persist_destroy(dmp2_engine* e);
@@ -271,6 +273,8 @@ int strip_stats_exchange(dmp2_engine* e, const float* gamma, float* norm_ss, cud
 int strip_halo_push(dmp2_engine* e, cudaStream_t st);
 int strip_halo_wait(dmp2_engine* e, cudaStream_t st);
 int strip_head_gather(dmp2_engine* e, cudaStream_t st);
+int strip_x3_gather(dmp2_engine* e, cudaStream_t st);                       // my rows of x3 -> every rank (side stream)
+int strip_vgru_gather(dmp2_engine* e, int c0, int c1, cudaStream_t st);      // columns [c0, c1) of v_last -> every rank
 // rows of the 2-D track this engine works on, and where its conv activations live
 struct Rows { int r0, R; };
 static inline Rows rows_of(const dmp2_engine* e, int L) {

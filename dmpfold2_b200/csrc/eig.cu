@@ -80,8 +80,8 @@ __device__ __forceinline__ double block_sum1(double v, double* scr) {
 template <int EIG_CL>
 __global__ void __launch_bounds__(EIG_THREADS, 1)
 k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* __restrict__ V, double* __restrict__ wk,
-           int rows_in_smem, int vec_in_smem, float* __restrict__ vals_out, float* __restrict__ mds_out,
-           float* __restrict__ vec_out) {
+           int rows_in_smem, int vec_in_smem, int pre_tridiag, int stage_rows, float* __restrict__ vals_out,
+           float* __restrict__ mds_out, float* __restrict__ vec_out) {
     cg::cluster_group cluster = cg::this_cluster();
     const int c = (int)cluster.block_rank();
     extern __shared__ double sm[];
@@ -91,6 +91,7 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
     double* se = sm + 5 * n;         // [n] off-diagonal of T
     double* se2 = sm + 6 * n;        // [n] e^2
     double* big = sm + 7 * n;        // matrix rows during phase 1, inverse-iteration vectors afterwards
+    if (pre_tridiag) { sd = sm; se = sm + n; se2 = sm + 2 * n; big = sm + 3 * n; }    // no Householder buffers needed
     __shared__ double red[33];
     __shared__ double lam[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -105,6 +106,12 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
     // phase timestamps (ns, %globaltimer) for dmp2_debug_eig_phases: start, tridiag, bisect, invit, done
     unsigned long long* stamps = reinterpret_cast<unsigned long long*>(wk + 35 * n);
     auto stamp = [&](int i) { if (c == 0 && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); stamps[i] = t; } };
+    // pre_tridiag: d, e, beta and V were produced by k_tridiag_grid; only CTA 0 has work left (no cluster barrier is
+    // executed by anybody on this path)
+    __shared__ double scr_a[EIG_THREADS / 32], scr_b[EIG_THREADS / 32];
+    if (pre_tridiag) {
+        if (c != 0) return;
+    } else {
     stamp(0);
     const int nloc = (n - c + EIG_CL - 1) / EIG_CL;
     double* rbase;
@@ -125,7 +132,6 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
     // ping-ponged by column parity; a CTA can run at most one gather ahead of its slowest peer.
     // The first component of the Householder vector (v0) is carried in a register, the gathered column is never
     // patched.
-    __shared__ double scr_a[EIG_THREADS / 32], scr_b[EIG_THREADS / 32];
     __shared__ __align__(8) unsigned long long gbar[4];          // [column gather | p gather][parity]
     const uint32_t gbar0 = cc::smem_u32(&gbar[0]);
     if (tid == 0) {
@@ -215,6 +221,7 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
     cluster.sync();
     if (c != 0) return;                                // phases 2-5 only touch global memory and CTA 0's smem
     stamp(1);
+    }
 
     for (int i = tid; i < n; i += EIG_THREADS) { sd[i] = gd[i]; se[i] = ge[i]; se2[i] = ge[i] * ge[i]; }
     __syncthreads();
@@ -262,9 +269,10 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
 
     stamp(2);
     // ---------------- 3. inverse iteration on T ---------------------------------------------------------
-    double* vecs = vec_in_smem ? big : gvec;
-    double* zs = vecs;               // [8][n] eigenvectors of T, then of M
-    double* u0 = zs + 8 * n;         // [8][n] LU of T - lambda I: three diagonals of U
+    // vec_in_smem: 0 = all work vectors in global memory, 1 = all 32 n doubles in shared memory,
+    //              2 = the 8 eigenvectors in shared memory, the LU factors in global memory (large n)
+    double* zs = vec_in_smem ? big : gvec;                       // [8][n] eigenvectors of T, then of M
+    double* u0 = (vec_in_smem == 1 ? big : gvec) + 8 * n;        // [8][n] LU of T - lambda I: three diagonals of U
     double* u1 = u0 + 8 * n;
     double* u2 = u1 + 8 * n;
     for (int i = tid; i < 8 * n; i += EIG_THREADS) {
@@ -352,16 +360,18 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
 
     stamp(3);
     // ---------------- 4. back-transform: z <- H_0 H_1 ... H_{n-3} z  (warp w owns vector w) --------------
-    // Reflectors are staged 16 at a time into shared memory by all warps (one L2 round trip per block instead of
-    // one per reflector) when the work vectors live in shared memory; otherwise they are read in place.
+    // Reflectors are staged `stage_rows` at a time into shared memory by all warps (one L2 round trip per block
+    // instead of one per reflector) when the eigenvectors live in shared memory; otherwise they are read in place.
     if (vec_in_smem) {
-        double* stage = u0;                            // 24 n doubles, free after the inverse iteration
-        for (int khi = n - 3; khi >= 0; khi -= 16) {
-            const int klo = khi - 15 > 0 ? khi - 15 : 0;
-            for (int r = warp; r <= khi - klo; r += NW) {
-                const int k = klo + r, m = n - k - 1;
-                const double* v = V + (int64_t)k * n;
-                for (int i = lane; i < m; i += 32) stage[r * n + i] = v[i];
+        double* stage = vec_in_smem == 1 ? u0 : big + 8 * n;      // mode 1: the 24 n doubles of the LU factors are free now
+        for (int khi = n - 3; khi >= 0; khi -= stage_rows) {
+            const int klo = khi - (stage_rows - 1) > 0 ? khi - (stage_rows - 1) : 0;
+            // all threads share the block of reflectors evenly, so the loads of one stage are one round of L2 latency
+            const int tot = (khi - klo + 1) * n;
+#pragma unroll 4
+            for (int idx = tid; idx < tot; idx += EIG_THREADS) {
+                const int r = idx / n, i = idx - r * n;
+                if (i < n - (klo + r) - 1) stage[idx] = __ldcg(V + (int64_t)(klo + r) * n + i);
             }
             __syncthreads();
             if (warp < 8) {
@@ -427,9 +437,166 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
     stamp(4);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Large L (the rows no longer fit a cluster's shared memory): Householder tridiagonalisation on the WHOLE GPU.
+// One CTA per SM (cooperative launch), matrix in global memory (L2-resident: 33 MB of fp64 at L = 2048), rows owned
+// cyclically by CTA.  The rank-2 update of step k and the matrix-vector product of step k+1 are fused into ONE pass
+// over the trailing matrix: every CTA first recomputes the updated row k+1 by itself (it only needs v, w and the old
+// row), which gives the next Householder vector v' without waiting for anybody; each owned row is then read once,
+// updated, written, and dotted with v' on the fly.  One grid-wide barrier per column (the all-gather of p' = A v'),
+// half the memory traffic of update-then-multiply.  Writes d, e, beta and the reflectors V exactly like phase 1 of
+// k_eig_top8, which then runs phases 2-5 (pre_tridiag = 1).
+// ---------------------------------------------------------------------------------------------------
+#define TG_THREADS 512
+constexpr int TG_NW = TG_THREADS / 32;
+
+__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// all threads of all CTAs; `target` = CTAs x barriers passed so far (monotonic counter, zeroed before the launch)
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
+        if (ld_acquire_gpu_u32(bar) < target) {
+            const long long t0 = clock64();
+            while (ld_acquire_gpu_u32(bar) < target) {
+                if (clock64() - t0 > 8000000000LL) { printf("k_tridiag_grid: grid barrier timed out\n"); __trap(); }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(TG_THREADS, 1)
+k_tridiag_grid(const float* __restrict__ M, int n, double* __restrict__ A, double* __restrict__ V, double* __restrict__ wk,
+               unsigned int* __restrict__ bar) {
+    const int G = gridDim.x, b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    extern __shared__ double sm[];
+    double* sv = sm;                 // [n] Householder vector of the column being eliminated (v[0] = v0)
+    double* sw = sm + n;             // [n] w = p - kk v
+    double* sv2 = sm + 2 * n;        // [n] next Householder vector
+    __shared__ double scr_a[TG_NW], scr_b[TG_NW], spart[TG_NW];
+    double* gd = wk;
+    double* ge = wk + n;
+    double* beta = wk + 2 * n;
+    double* pbuf = wk + 40 * (int64_t)n;                 // [2][n] gathered p' (ping-pong by column parity)
+    unsigned long long* stamps = reinterpret_cast<unsigned long long*>(wk + 35 * (int64_t)n);
+    if (b == 0 && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); stamps[0] = t; }
+    unsigned int nbar = 0;
+
+    for (int i = b; i < n; i += G) {                     // fp32 -> fp64, owned rows
+        const float* src = M + (int64_t)i * n;
+        double* dst = A + (int64_t)i * n;
+        for (int j = tid; j < n; j += TG_THREADS) dst[j] = (double)src[j];
+    }
+    for (int j = tid; j < n; j += TG_THREADS) { sv[j] = 0.0; sw[j] = 0.0; }
+    grid_barrier(bar, (unsigned)G * ++nbar);
+
+    // iteration k eliminates nothing itself: it applies the update of column k (v, w; none for k = -1) and prepares
+    // column k+1 (d, e, v', p').  m = rows/columns of the trailing matrix A[k+1.., k+1..].
+    for (int k = -1; k <= n - 3; k++) {
+        const int m = n - k - 1;
+        const int c0 = k + 1;                                                 // first trailing row / column
+        // ---- updated row c0, recomputed by every CTA: r[j] = A[c0][c0+j] - (v[0] w[j] + w[0] v[j])
+        const double* r0 = A + (int64_t)c0 * n + c0;
+        const double v_0 = sv[0], w_0 = sw[0];
+        double part = 0.0;
+        for (int j = tid; j < m; j += TG_THREADS) {
+            const double r = __ldcg(r0 + j) - (v_0 * sw[j] + w_0 * sv[j]);
+            if (j == 0) { if (b == 0) gd[c0] = r; }
+            else { sv2[j - 1] = r; part += r * r; }
+        }
+        const double sigma = block_sum1(part, scr_a);                         // includes the barrier that publishes sv2
+        double bt2 = 0.0;
+        const int m2 = m - 1;                                                 // length of the next Householder vector
+        if (m >= 3) {
+            const double x0 = sv2[0];
+            const double tail = sigma - x0 * x0;
+            const bool reflect = tail > 0.0;
+            const double alpha = reflect ? ((x0 >= 0.0) ? -sqrt(sigma) : sqrt(sigma)) : x0;
+            const double v0 = x0 - alpha;
+            bt2 = reflect ? 2.0 / (tail + v0 * v0) : 0.0;
+            __syncthreads();                                                  // everyone has read sv2[0]
+            if (tid == 0) sv2[0] = v0;
+            if (b == 0 && tid == 0) { ge[c0] = alpha; beta[c0] = bt2; }
+            __syncthreads();
+            if (b == 0) for (int j = tid; j < m2; j += TG_THREADS) V[(int64_t)c0 * n + j] = sv2[j];
+        } else {                                                              // last 2 x 2 block: no reflector left
+            if (b == 0 && tid == 0) { ge[c0] = sv2[0]; ge[n - 1] = 0.0; }
+            __syncthreads();
+            if (tid == 0) sv2[0] = 0.0;
+            __syncthreads();
+        }
+        // ---- one pass over the owned rows i > c0: update with (v, w), then dot with v'
+        double* pout = pbuf + (int64_t)((k + 1) & 1) * n;
+        const int first = c0 + 1 + ((b - (c0 + 1)) % G + G) % G;             // smallest owned row index > c0
+        const int nl = first < n ? (n - 1 - first) / G + 1 : 0;               // owned trailing rows
+        int W = TG_NW;                                                        // warps cooperating on one row
+        while (W > 1 && nl * W > TG_NW) W >>= 1;
+        const int per_round = TG_NW / W, grp = warp / W, sub = warp % W;
+        for (int base = 0; base < nl; base += per_round) {
+            const int lr = base + grp;
+            double acc = 0.0;
+            int i = 0;
+            if (lr < nl) {
+                i = first + lr * G;
+                const int ti = i - c0;
+                double* row = A + (int64_t)i * n + c0;
+                const double vi = sv[ti], wi = sw[ti];
+                const int S = 32 * W;
+                int j = 1 + sub * 32 + lane;
+                for (; j + 3 * S < m; j += 4 * S) {
+                    double a0 = __ldcg(row + j), a1 = __ldcg(row + j + S), a2 = __ldcg(row + j + 2 * S), a3 = __ldcg(row + j + 3 * S);
+                    a0 -= vi * sw[j] + wi * sv[j];
+                    a1 -= vi * sw[j + S] + wi * sv[j + S];
+                    a2 -= vi * sw[j + 2 * S] + wi * sv[j + 2 * S];
+                    a3 -= vi * sw[j + 3 * S] + wi * sv[j + 3 * S];
+                    __stcg(row + j, a0); __stcg(row + j + S, a1); __stcg(row + j + 2 * S, a2); __stcg(row + j + 3 * S, a3);
+                    acc += a0 * sv2[j - 1] + a1 * sv2[j + S - 1] + a2 * sv2[j + 2 * S - 1] + a3 * sv2[j + 3 * S - 1];
+                }
+                for (; j < m; j += S) {
+                    double a0 = __ldcg(row + j) - (vi * sw[j] + wi * sv[j]);
+                    __stcg(row + j, a0);
+                    acc += a0 * sv2[j - 1];
+                }
+                acc = warp_sum(acc);
+            }
+            if (lane == 0) spart[warp] = acc;
+            __syncthreads();
+            if (lr < nl && sub == 0 && lane == 0) {
+                double t = 0.0;
+                for (int q = 0; q < W; q++) t += spart[warp + q];
+                pout[i - c0 - 1] = t * bt2;
+            }
+            __syncthreads();
+        }
+        grid_barrier(bar, (unsigned)G * ++nbar);
+        if (k == n - 3) break;
+        // ---- gathered p' -> w' = p' - kk' v'; v <- v'
+        double pv = 0.0;
+        for (int j = tid; j < m2; j += TG_THREADS) {
+            const double pj = __ldcg(pout + j);
+            sw[j] = pj;
+            pv += pj * sv2[j];
+        }
+        const double kk = 0.5 * bt2 * block_sum1(pv, scr_b);
+        for (int j = tid; j < m2; j += TG_THREADS) { const double vj = sv2[j]; sw[j] -= kk * vj; sv[j] = vj; }
+        __syncthreads();
+    }
+    if (b == 0 && tid == 0) {
+        gd[n - 1] = __ldcg(A + (int64_t)(n - 1) * n + (n - 1));
+        unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); stamps[1] = t;
+    }
+}
+
 template <int CL>
-static int launch_eig(dmp2_engine* e, const float* m, int L, int rows_in_smem, int vec_in_smem, size_t smem, float* vals,
-                      float* mds_scaled, float* vecs_raw, cudaStream_t st) {
+static int launch_eig(dmp2_engine* e, const float* m, int L, int rows_in_smem, int vec_in_smem, int pre_tridiag, size_t smem,
+                      float* vals, float* mds_scaled, float* vecs_raw, cudaStream_t st, int stage_rows = 16) {
     double* V = e->ws.eig_a + (int64_t)L * L;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(CL);
@@ -441,7 +608,7 @@ static int launch_eig(dmp2_engine* e, const float* m, int L, int rows_in_smem, i
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    CUDA_TRY(e, cudaLaunchKernelEx(&cfg, k_eig_top8<CL>, m, L, e->ws.eig_a, V, e->ws.eig_w, rows_in_smem, vec_in_smem, vals,
+    CUDA_TRY(e, cudaLaunchKernelEx(&cfg, k_eig_top8<CL>, m, L, e->ws.eig_a, V, e->ws.eig_w, rows_in_smem, vec_in_smem, pre_tridiag, stage_rows, vals,
                                    mds_scaled, vecs_raw));
     POST_LAUNCH(e, "k_eig_top8");
     return 0;
@@ -472,16 +639,42 @@ int run_eig_top8(dmp2_engine* e, const float* m, int L, float* vals, float* mds_
     size_t s8, s16;
     plan(8, r8, v8, s8);
     static const bool force16 = getenv("DMP2_EIG_CL") && atoi(getenv("DMP2_EIG_CL")) == 16;   // tuning knob
-    if (r8 && !force16) return launch_eig<8>(e, m, L, r8, v8, s8, vals, mds_scaled, vecs_raw, st);
+    if (r8 && !force16) return launch_eig<8>(e, m, L, r8, v8, 0, s8, vals, mds_scaled, vecs_raw, st);
     plan(16, r16, v16, s16);
+    // rows do not even fit a 16-CTA cluster: tridiagonalise on the whole GPU, then phases 2-5 in one CTA
+    static const bool no_grid = getenv("DMP2_EIG_GRID") && atoi(getenv("DMP2_EIG_GRID")) == 0;       // tuning knob
+    if (!r16 && !no_grid && 3 * n * 8 <= LIMIT) {
+        if (!e->attr_eig_grid) {
+            CUDA_TRY(e, cudaFuncSetAttribute(k_tridiag_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LIMIT));
+            e->attr_eig_grid = true;
+        }
+        double* Vg = e->ws.eig_a + (int64_t)L * L;
+        unsigned int* bar = reinterpret_cast<unsigned int*>(e->ws.eig_w + 42 * (int64_t)L);
+        CUDA_TRY(e, cudaMemsetAsync(bar, 0, sizeof(unsigned int), st));
+        int n_arg = L;
+        const float* m_arg = m;
+        double* a_arg = e->ws.eig_a;
+        double* wk_arg = e->ws.eig_w;
+        void* args[6] = {(void*)&m_arg, (void*)&n_arg, (void*)&a_arg, (void*)&Vg, (void*)&wk_arg, (void*)&bar};
+        CUDA_TRY(e, cudaLaunchCooperativeKernel((const void*)k_tridiag_grid, dim3(e->num_sms), dim3(TG_THREADS), args, 3 * n * 8, st));
+        POST_LAUNCH(e, "k_tridiag_grid");
+        // phases 2-5 in CTA 0: d, e, e^2 (3 n) + as much of the work vectors as fits
+        const size_t cap = LIMIT / 8;
+        int vmode = 0, srows = 16;
+        size_t words = 3 * n;
+        if (35 * n <= cap) { vmode = 1; words = 35 * n; }
+        else if (13 * n <= cap) { vmode = 2; srows = (int)std::min<size_t>(16, (cap - 11 * n) / n); words = (11 + srows) * n; }
+        if (words > cap) return e->fail(DMP2_ERR_UNSUPPORTED, "eig_top8: L too large");
+        return launch_eig<8>(e, m, L, 0, vmode, 1, words * 8, vals, mds_scaled, vecs_raw, st, srows);
+    }
     if (s16 > LIMIT) return e->fail(DMP2_ERR_UNSUPPORTED, "eig_top8: L too large");
     if (!e->eig_no_cl16) {
-        if (launch_eig<16>(e, m, L, r16, v16, s16, vals, mds_scaled, vecs_raw, st) == 0) return 0;
+        if (launch_eig<16>(e, m, L, r16, v16, 0, s16, vals, mds_scaled, vecs_raw, st) == 0) return 0;
         cudaGetLastError();                              // 16-CTA clusters not schedulable here: use 8 from now on
         e->eig_no_cl16 = true;
         e->status = 0;
         e->err.clear();
     }
     if (s8 > LIMIT) return e->fail(DMP2_ERR_UNSUPPORTED, "eig_top8: L too large");
-    return launch_eig<8>(e, m, L, r8, v8, s8, vals, mds_scaled, vecs_raw, st);
+    return launch_eig<8>(e, m, L, r8, v8, 0, s8, vals, mds_scaled, vecs_raw, st);
 }

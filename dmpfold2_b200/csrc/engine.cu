@@ -337,9 +337,19 @@ static int fold_impl(dmp2_engine* e, const uint8_t* msa, int N, int L, const flo
     TRY(run_reweight(e, msa, N, L, ws.seqw, e->side));
     TRY(run_dca(e, msa, N, L, ws.seqw, ws.feat, e->side));
     CUDA_TRY(e, cudaEventRecord(e->ev_join, e->side));
-    TRY(run_vgru(e, msa, N, L, ws.v_last, st));
+    float* v_last = ws.v_last;
+    if (e->strip_on && e->sp.world > 1 && e->vgru_mode == 0) {
+        // halo-sharded: the scan is independent per alignment column, so every rank takes a range of columns
+        StripCtx& sp = e->sp;
+        v_last = reinterpret_cast<float*>(sp.win + sp.off_vlast);
+        const int cper = cdiv(L, sp.world), c0 = std::min(L, sp.rank * cper), c1 = std::min(L, c0 + cper);
+        if (c1 > c0) TRY(run_vgru_tc(e, msa + c0, N, c1 - c0, v_last + (int64_t)c0 * 512, st, L));
+        TRY(strip_vgru_gather(e, c0, c1, st));
+    } else {
+        TRY(run_vgru(e, msa, N, L, ws.v_last, st));
+    }
     mark();
-    TRY(run_bigru(e, e->w.hgru, 2, ws.v_last, L, ws.mat1d_t, st));
+    TRY(run_bigru(e, e->w.hgru, 2, v_last, L, ws.mat1d_t, st));
     mark();
     CUDA_TRY(e, cudaStreamWaitEvent(st, e->ev_join, 0));
     mark();

@@ -124,7 +124,9 @@ struct GramEpilogue {
 };
 struct WoodburyEpilogue {
     float* c; int64_t ld; const float* scal;
+    int m0;                              // first row of the inverse this launch computes (0 unless halo-sharded)
     __device__ void operator()(int m, int n, float4 v) const {
+        m += m0;
         float r = 1.0f / scal[2];
         float4 o = make_float4(-v.x * r, -v.y * r, -v.z * r, -v.w * r);
         if (m == n) o.x += r;
@@ -237,9 +239,9 @@ __global__ void __launch_bounds__(256) k_gj_panels(float* __restrict__ a, int64_
 // inverse covariance -> features                                                        (predict.py:54-61)
 // ---------------------------------------------------------------------------------------------------
 // feat[(i*L+j)][a*21+b] = inv[i*21+a][j*21+b];  x3[i][j] = ||inv[i,:20,j,:20]||_F (0 on the diagonal)
-__global__ void __launch_bounds__(128) k_feat_gather(const float* __restrict__ inv, int64_t ld, int L, float* __restrict__ feat,
+__global__ void __launch_bounds__(128) k_feat_gather(const float* __restrict__ inv, int64_t ld, int L, int i0, float* __restrict__ feat,
                                                      float* __restrict__ x3) {
-    int i = blockIdx.y, j = blockIdx.x;
+    int i = blockIdx.y + i0, j = blockIdx.x;
     __shared__ float red[4];
     float ss = 0.f;
     float* out = feat + ((int64_t)i * L + j) * DMP2_FEAT_LD;
@@ -285,9 +287,11 @@ __global__ void __launch_bounds__(1024) k_apc_total(int L, float* __restrict__ a
     }
     if (threadIdx.x == 0) apc[2 * L] = (float)red[0];
 }
-__global__ void k_apc_apply(const float* __restrict__ x3, const float* __restrict__ apc, int L, float* __restrict__ feat) {
+__global__ void k_apc_apply(const float* __restrict__ x3, const float* __restrict__ apc, int L, int first, int count,
+                            float* __restrict__ feat) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= L * L) return;
+    if (idx >= count) return;
+    idx += first;
     int i = idx / L, j = idx - i * L;
     float v = (i == j) ? 0.f : x3[idx] - apc[j] * apc[L + i] / apc[2 * L];
     feat[(int64_t)idx * DMP2_FEAT_LD + 441] = v;
@@ -358,6 +362,11 @@ int run_dca(dmp2_engine* e, const uint8_t* msa, int N, int L, const float* w, fl
     POST_LAUNCH(e, "k_col_mean");
     const int Npad64 = (N + 63) & ~63, n4 = (n + 3) & ~3;
     const bool woodbury = Npad64 < npad;       // N < 21 L: invert the N x N Gram system instead (Woodbury identity)
+    // halo-sharded fold: the last (and largest) product of the Woodbury path, the feature gather and the APC term are
+    // restricted to this rank's rows; the contact-norm map is completed through the window (strip.cu)
+    const bool shard = e->strip_on && e->sp.world > 1 && woodbury;
+    const Rows rw = shard ? rows_of(e, L) : Rows{0, L};
+    float* x3 = shard ? reinterpret_cast<float*>(e->sp.win + e->sp.off_x3) : ws.x3;
     if (woodbury && n4 != n) CUDA_TRY(e, cudaMemsetAsync(ws.xct, 0, (size_t)Npad * n4 * sizeof(float), st));   // pad columns
     k_center<<<dim3(cdiv(Npad, 256), L), 256, 0, st>>>(ws.msa_t, w, mean, N, Npad, ws.xc, woodbury ? ws.xct : nullptr, n4);
     POST_LAUNCH(e, "k_center");
@@ -379,16 +388,19 @@ int run_dca(dmp2_engine* e, const uint8_t* msa, int N, int L, const float* w, fl
         TRY(gj_invert(e, ws.kmat, Npad64, st));
         sgemm_launch<8>(Npad, n4, Npad, LoadRowMajorK{ws.kmat, Npad64}, LoadColMajorN{ws.xct, n4}, StoreRowMajor{ws.wy, n4, nullptr, 1.0f}, st);
         POST_LAUNCH(e, "sgemm<woodbury_y>");
-        sgemm_launch<8>(n, n4, Npad, LoadRowMajorK{ws.xc, Npad}, LoadColMajorN{ws.wy, n4}, WoodburyEpilogue{ws.cov, npad, ws.scal}, st);
+        // halo-sharded: only the rows of the inverse that feed this rank's strip of the pair features
+        sgemm_launch<8>(21 * rw.R, n4, Npad, LoadRowMajorK{ws.xc + (int64_t)21 * rw.r0 * Npad, Npad}, LoadColMajorN{ws.wy, n4},
+                        WoodburyEpilogue{ws.cov, npad, ws.scal, 21 * rw.r0}, st);
         POST_LAUNCH(e, "sgemm<woodbury_inv>");
     }
-    k_feat_gather<<<dim3(L, L), 128, 0, st>>>(ws.cov, npad, L, feat444, ws.x3);
+    k_feat_gather<<<dim3(L, rw.R), 128, 0, st>>>(ws.cov, npad, L, rw.r0, feat444, x3);
     POST_LAUNCH(e, "k_feat_gather");
-    k_apc_sums<<<2 * L, 256, 0, st>>>(ws.x3, L, ws.apc);
+    if (shard) TRY(strip_x3_gather(e, st));             // APC needs the sums over ALL rows
+    k_apc_sums<<<2 * L, 256, 0, st>>>(x3, L, ws.apc);
     POST_LAUNCH(e, "k_apc_sums");
     k_apc_total<<<1, 1024, 0, st>>>(L, ws.apc);
     POST_LAUNCH(e, "k_apc_total");
-    k_apc_apply<<<cdiv(L * L, 256), 256, 0, st>>>(ws.x3, ws.apc, L, feat444);
+    k_apc_apply<<<cdiv(rw.R * L, 256), 256, 0, st>>>(x3, ws.apc, L, rw.r0 * L, rw.R * L, feat444);
     POST_LAUNCH(e, "k_apc_apply");
     return 0;
 }

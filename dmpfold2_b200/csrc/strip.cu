@@ -105,11 +105,11 @@ uint32_t* flag_ptr(const StripCtx& sp, int dst_rank, int kind, int src_rank) {
     return reinterpret_cast<uint32_t*>(sp.peer[dst_rank] + sp.off_flags) + kind * DMP2_MAX_RANKS + src_rank;
 }
 
-int launch_push(dmp2_engine* e, PushArgs& a, cudaStream_t st) {
+int launch_push(dmp2_engine* e, PushArgs& a, cudaStream_t st, int ticket = 0) {
     unsigned long long maxb = 0;
     for (int i = 0; i < a.nseg; i++) maxb = std::max(maxb, a.seg[i].bytes);
     int gx = (int)std::min<unsigned long long>(std::max<unsigned long long>(maxb / (16 * 256 * 4), 1), 32);
-    k_push<<<dim3(gx, a.nseg), 256, 0, st>>>(a, e->sp.ticket);
+    k_push<<<dim3(gx, a.nseg), 256, 0, st>>>(a, e->sp.ticket + ticket);
     POST_LAUNCH(e, "k_push");
     return 0;
 }
@@ -142,6 +142,8 @@ int strip_setup(dmp2_engine* e, int rank, int world, int L, unsigned char* handl
     for (int i = 0; i < 4; i++) { sp.off_act[i] = off; off = align_up(off + px * esz[i], 1024); }
     sp.off_stats = off; off = align_up(off + (size_t)2 * DMP2_MAX_RANKS * 256 * sizeof(double), 1024);
     sp.off_head = off; off = align_up(off + (size_t)2 * L * L * sizeof(float), 1024);
+    sp.off_x3 = off; off = align_up(off + (size_t)L * L * sizeof(float), 1024);
+    sp.off_vlast = off; off = align_up(off + (size_t)L * 512 * sizeof(float), 1024);
     sp.off_flags = off; off = align_up(off + (size_t)STRIP_NFLAGS * DMP2_MAX_RANKS * sizeof(uint32_t), 1024);
     sp.win_bytes = off;
     CUDA_TRY(e, cudaMalloc(&sp.win, sp.win_bytes));
@@ -283,6 +285,53 @@ int strip_head_gather(dmp2_engine* e, cudaStream_t st) {
     }
     TRY(launch_push(e, a, st));
     k_wait<<<1, 32, 0, st>>>(reinterpret_cast<const uint32_t*>(sp.win + sp.off_flags) + STRIP_FLAG_HEAD * DMP2_MAX_RANKS, mask, ep);
+    POST_LAUNCH(e, "k_wait");
+    return 0;
+}
+
+// vgru is independent per alignment column (network.py:223-224: the MSA columns are its batch): every rank scans a
+// range of columns and stores its rows of the (L, 512) result into every window
+int strip_vgru_gather(dmp2_engine* e, int c0, int c1, cudaStream_t st) {
+    StripCtx& sp = e->sp;
+    const uint32_t ep = ++sp.epoch[STRIP_FLAG_VGRU];
+    if (sp.world == 1) return 0;
+    PushArgs a;
+    a.nseg = 0; a.nflag = 0; a.epoch = ep; a.words = 0;
+    uint32_t mask = 0;
+    const size_t first = sp.off_vlast + (size_t)c0 * 512 * sizeof(float), bytes = (size_t)std::max(c1 - c0, 0) * 512 * sizeof(float);
+    for (int r = 0; r < sp.world; r++) {
+        if (r == sp.rank) continue;
+        if (bytes) a.seg[a.nseg++] = {sp.win + first, sp.peer[r] + first, bytes};
+        a.flag[a.nflag++] = flag_ptr(sp, r, STRIP_FLAG_VGRU, sp.rank);
+        mask |= 1u << r;
+    }
+    if (a.nseg == 0) a.seg[a.nseg++] = {sp.win + sp.off_vlast, sp.win + sp.off_vlast, 0};      // nothing to send, flags only
+    TRY(launch_push(e, a, st));
+    k_wait<<<1, 32, 0, st>>>(reinterpret_cast<const uint32_t*>(sp.win + sp.off_flags) + STRIP_FLAG_VGRU * DMP2_MAX_RANKS, mask, ep);
+    POST_LAUNCH(e, "k_wait");
+    return 0;
+}
+
+// DCA tail: every rank forms only its rows of the inverse covariance, hence only its rows of the contact-norm map
+// x3; the APC term (predict.py:57-60) needs the row and column sums of the whole map.  Runs on the engine's side
+// stream (second ticket word), concurrently with the vgru exchange on the main stream.
+int strip_x3_gather(dmp2_engine* e, cudaStream_t st) {
+    StripCtx& sp = e->sp;
+    const uint32_t ep = ++sp.epoch[STRIP_FLAG_X3];
+    if (sp.world == 1) return 0;
+    const size_t first = sp.off_x3 + (size_t)sp.r0 * sp.L * sizeof(float), bytes = (size_t)(sp.r1 - sp.r0) * sp.L * sizeof(float);
+    PushArgs a;
+    a.nseg = 0; a.nflag = 0; a.epoch = ep;
+    a.words = ((first | bytes) & 15) ? 1 : 0;
+    uint32_t mask = 0;
+    for (int r = 0; r < sp.world; r++) {
+        if (r == sp.rank) continue;
+        a.seg[a.nseg++] = {sp.win + first, sp.peer[r] + first, bytes};
+        a.flag[a.nflag++] = flag_ptr(sp, r, STRIP_FLAG_X3, sp.rank);
+        mask |= 1u << r;
+    }
+    TRY(launch_push(e, a, st, 1));
+    k_wait<<<1, 32, 0, st>>>(reinterpret_cast<const uint32_t*>(sp.win + sp.off_flags) + STRIP_FLAG_X3 * DMP2_MAX_RANKS, mask, ep);
     POST_LAUNCH(e, "k_wait");
     return 0;
 }

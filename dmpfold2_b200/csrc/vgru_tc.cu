@@ -233,7 +233,9 @@ int make_map2d(dmp2_engine* e, CUtensorMap* m, const __half* ptr, int rows, int 
 
 }  // namespace
 
-int run_vgru_tc(dmp2_engine* e, const uint8_t* msa, int N, int L, float* out, cudaStream_t st) {
+// L alignment columns starting at msa[0] (row stride ld): a column range of a wider alignment when ld > L
+int run_vgru_tc(dmp2_engine* e, const uint8_t* msa, int N, int L, float* out, cudaStream_t st, int ld) {
+    if (ld <= 0) ld = L;
     if (!e->vt_state) e->vt_state = new VtState();
     VtState* S = (VtState*)e->vt_state;
     const Weights& w = e->w;
@@ -268,7 +270,7 @@ int run_vgru_tc(dmp2_engine* e, const uint8_t* msa, int N, int L, float* out, cu
     for (int s = 0; s < N + 2; s++) {
         VtParams p;
         p.L = L;
-        p.codes = msa + (int64_t)std::min(s, N - 1) * L;
+        p.codes = msa + (int64_t)std::min(s, N - 1) * ld;
         // role 0: time t = s, h0 state before t lives in buffer (s & 1)
         p.role[0] = {s < N, s & 1, w.vt_bias[0], w.vt_gi0, hf[s & 1], hf[(s + 1) & 1], hi((s + 1) & 1), lo((s + 1) & 1)};
         // role 1: time t = s-1, input h0[t] = buffer (s & 1)

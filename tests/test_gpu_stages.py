@@ -147,7 +147,7 @@ def test_head_mds_on_golden_head(eng):
     assert (mds.cpu() - torch.from_numpy(g['mds'])).abs().max() < 3e-3
 
 
-@pytest.mark.parametrize('l', [8, 33, 150])
+@pytest.mark.parametrize('l', [8, 33, 150, 520, 700, 1100])      # cluster of 8, of 16, whole-GPU tridiagonalisation
 def test_eig_top8_against_fp64_eigh(eng, l):
     g = torch.Generator().manual_seed(l)
     q, _ = torch.linalg.qr(torch.randn(l, l, generator=g, dtype=torch.float64))
