@@ -152,3 +152,27 @@ def test_pdb_writer_is_byte_exact_against_the_reference_cli():
     want = open(os.path.join(GOLDEN, 'pf10963_n0_m0.pdb')).read()
     got = P.format_pdb(torch.from_numpy(g['coords']), torch.from_numpy(g['confs']), g['alnmat'])
     assert got == want
+
+
+def test_strip_partition_is_pure_host_arithmetic():
+    """dmp2_strip_rows (include/dmp2.h): row strips of a halo-sharded fold -- callable without a GPU."""
+    from dmpfold2_b200.engine import strip_rows
+    for l in (16, 82, 100, 300, 1024, 2048, 2051):
+        for world in (1, 2, 3, 4, 8):
+            try:
+                parts = [strip_rows(l, world, r) for r in range(world)]
+            except ValueError:
+                per = -(-(-(-l // 8)) // world) * 8                                   # ceil(ceil(l / 8) / world) * 8
+                assert world > 1 and (world - 1) * per + 2 > l                        # too short for that many strips
+                continue
+            assert parts[0][0] == 0 and parts[-1][1] == l
+            assert all(parts[r][1] == parts[r + 1][0] for r in range(world - 1))      # contiguous cover
+            assert all(a % 8 == 0 for a, _ in parts)                                  # conv tile rows
+            assert all(b - a >= 2 for a, b in parts)                                  # every strip can feed a 2-row halo
+            assert len({b - a for a, b in parts[:-1]}) <= 1                           # equal strips, the last takes the rest
+    with pytest.raises(ValueError):
+        strip_rows(40, 8, 0)
+    with pytest.raises(ValueError):
+        strip_rows(300, 9, 0)
+    with pytest.raises(ValueError):
+        strip_rows(300, 4, 4)

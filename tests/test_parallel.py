@@ -22,6 +22,7 @@ def test_round_robin_shards_partition_the_targets():
     assert P.world() == (0, 1)
     assert P.max_over_ranks(3.5) == 3.5
     assert P.fold_many([1, 2, 3], lambda t: t * 10) == [10, 20, 30]
+    assert P.exchange_handles(b'x' * 64) == [b'x' * 64]
 
 
 def _free_port():
@@ -47,6 +48,8 @@ def _worker(rank, world_size, port, out_dir):
         assert all(float(r['coords'][0, 0, 0]) == r['target'] for r in res)
         local = P.fold_many(list(range(5)), fake_fold, gather=False)
         assert [x is not None for x in local] == [t % world_size == rank for t in range(5)]
+        handles = P.exchange_handles(bytes([rank]) * 64)                  # the one-off window-handle exchange of a StripGroup
+        assert handles == [bytes([r]) * 64 for r in range(world_size)]
         slow = P.max_over_ranks(10.0 + rank)                             # device time = max over ranks
         assert slow == 10.0 + world_size - 1
         with open(os.path.join(out_dir, f'ok{rank}'), 'w') as fh:
