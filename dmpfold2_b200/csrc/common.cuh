@@ -212,6 +212,7 @@ struct dmp2_engine {
     bool eig_no_cl16 = false;        // set when a 16-CTA cluster launch was refused
     bool attr_eig = false, attr_refine = false, attr_eig_grid = false;   // per-engine (= per-device) cudaFuncSetAttribute done
     StripCtx sp;                     // halo-sharded mode: window + peers (strip.cu)
+    bool fuse_stats = false;         // DMP2_FUSE_STATS=1: InstanceNorm sums in the conv epilogue instead of k_in_stats (tested, not faster)
     bool strip_on = false;           // true while dmp2_fold_strip runs: the 2-D track works on rows [sp.r0, sp.r1)
     bool profile = false;            // record a CUDA-event pair around every conv launch (bench.py roofline)
     std::vector<cudaEvent_t> prof_ev;
@@ -245,14 +246,15 @@ int run_coord_head(dmp2_engine* e, const float* mat1d_t, const float* mds, int L
 int run_stem_base(dmp2_engine* e, const float* mat1d_t, const float* feat444, int L, cudaStream_t st);
 int run_stem_update(dmp2_engine* e, const float* dmap, int L, cudaStream_t st);   // -> ws.x (+ xh, xl)
 int run_conv_ffma(dmp2_engine* e, int blk, const float* x, int L, float* raw, cudaStream_t st);
-int run_norm_gate(dmp2_engine* e, int blk, const float* raw, float* x, int L, bool stem, cudaStream_t st);
+int run_norm_gate(dmp2_engine* e, int blk, const float* raw, float* x, int L, bool stem, cudaStream_t st, bool have_stats = false);
 int run_split_half(dmp2_engine* e, const float* x, int64_t n, __half* hi, __half* lo, uint8_t* x8lo, uint8_t* x8hi, cudaStream_t st);
 int run_resblock(dmp2_engine* e, int blk, int L, cudaStream_t st);                // ws.x -> ws.x
 int run_head(dmp2_engine* e, const float* x, int L, float* head2, cudaStream_t st);
 int run_head_post(dmp2_engine* e, const float* head2, int L, float* conf, float* mmat, cudaStream_t st);
 // conv_tc.cu
 int run_conv_tc(dmp2_engine* e, int blk, const __half* xh, const __half* xl, const uint8_t* x8lo, const uint8_t* x8hi, int L,
-                int H, int y_off, int map_rows, float* raw, int mode, cudaStream_t st);
+                int H, int y_off, int map_rows, float* raw, int mode, cudaStream_t st, bool fuse_stats = false);
+bool conv_tc_fuses_stats(const dmp2_engine* e);      // true: run_conv_tc(..., fuse_stats = true) leaves ws.norm_ss / sp.totals ready
 int run_gemm_tn_test(dmp2_engine* e, const float* a, const float* b, int M, int N, int K, int mode, float* c, cudaStream_t st);
 void conv_tc_destroy(dmp2_engine* e);
 // eig.cu

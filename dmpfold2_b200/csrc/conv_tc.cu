@@ -57,7 +57,18 @@ struct TcParams {
     int M;               // gemm: rows
     float* out;          // conv: raw [L*L][128]; gemm: C [M][512]
     const float* bias;   // conv: [512]
+    // fused InstanceNorm statistics of the output (network.py:32), nullptr = off: every CTA leaves the fp64 sums of
+    // its tile in stat_part, the last CTA of a group folds the group, the last group finishes (same deterministic
+    // two-level fold as k_in_stats, which this replaces after a conv)
+    double* stat_part;           // [grid + groups][256]
+    unsigned int* ticket;        // [1 + groups], zero between launches
+    float* norm;                 // [mean 128 | gamma * rstd 128]
+    const float* gamma;
+    double* totals;              // halo-sharded: [sum 128 | sumsq 128] of this launch instead of norm
+    double npix;                 // pixels the statistics are over (H * L)
 };
+constexpr int STAT_GROUP = 32;   // CTAs per first-level fold
+constexpr int STAT_LD = 132;     // floats per pixel row of the staged tile (conflict-free 16-byte stores)
 
 using namespace tc;
 
@@ -258,6 +269,77 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv5_tc(const __grid_consta
                 float4* dst = reinterpret_cast<float4*>(p.out + row * 128 + ch * 8);
                 dst[0] = make_float4(o[0], o[1], o[2], o[3]);
                 dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+                if (p.stat_part) {                   // stage the tile for the per-channel sums (operand rings are idle now)
+                    float4* sd4 = reinterpret_cast<float4*>(smem_gen + (size_t)(r * STAT_LD + ch * 8) * 4);
+                    sd4[0] = make_float4(o[0], o[1], o[2], o[3]); sd4[1] = make_float4(o[4], o[5], o[6], o[7]);
+                }
+            }
+        }
+        if (!p.gemm && p.stat_part) {
+            float* tile = reinterpret_cast<float*>(smem_gen);
+            if (!valid) {                            // pixels outside the image count as zeros
+                for (int c = 0; c < 128; c += 4) *reinterpret_cast<float4*>(tile + r * STAT_LD + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const int t = r;                         // this thread now owns channel t
+            double s4[4] = {0, 0, 0, 0}, q4[4] = {0, 0, 0, 0};        // four independent chains, combined in a fixed order
+#pragma unroll 4
+            for (int px = 0; px < TILE_M; px += 4) {
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const double v = (double)tile[(px + u) * STAT_LD + t];
+                    s4[u] += v;
+                    q4[u] += v * v;
+                }
+            }
+            const double s = (s4[0] + s4[1]) + (s4[2] + s4[3]), ss = (q4[0] + q4[1]) + (q4[2] + q4[3]);
+            double* part = p.stat_part;
+            part[(int64_t)blockIdx.x * 256 + t] = s;
+            part[(int64_t)blockIdx.x * 256 + 128 + t] = ss;
+            // deterministic two-level fold: last CTA of a group folds the group, last group folds the group sums
+            const unsigned G = STAT_GROUP, grp_id = blockIdx.x / G, ngrp = (gridDim.x + G - 1) / G;
+            const unsigned gfirst = grp_id * G, gsize = min(G, gridDim.x - gfirst);
+            double* part2 = part + (int64_t)gridDim.x * 256;
+            int* stage = reinterpret_cast<int*>(tile + TILE_M * STAT_LD);      // one word past the staged tile
+            __threadfence();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (t == 0) *stage = (atomicAdd(p.ticket + 1 + grp_id, 1u) == gsize - 1) ? 1 : 0;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (*stage != 0) {
+                __threadfence();
+                double a = 0.0, b = 0.0;
+#pragma unroll 8
+                for (unsigned q2 = 0; q2 < gsize; q2++) {
+                    a += __ldcg(part + (int64_t)(gfirst + q2) * 256 + t);
+                    b += __ldcg(part + (int64_t)(gfirst + q2) * 256 + 128 + t);
+                }
+                part2[(int64_t)grp_id * 256 + t] = a;
+                part2[(int64_t)grp_id * 256 + 128 + t] = b;
+                __threadfence();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (t == 0) {
+                    p.ticket[1 + grp_id] = 0;
+                    *stage = (atomicAdd(p.ticket, 1u) == ngrp - 1) ? 2 : 1;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (*stage == 2) {
+                    __threadfence();
+                    a = 0.0; b = 0.0;
+#pragma unroll 8
+                    for (unsigned q2 = 0; q2 < ngrp; q2++) {
+                        a += __ldcg(part2 + (int64_t)q2 * 256 + t);
+                        b += __ldcg(part2 + (int64_t)q2 * 256 + 128 + t);
+                    }
+                    if (p.totals) { p.totals[t] = a; p.totals[128 + t] = b; }
+                    else {
+                        const double mean = a / p.npix;
+                        double var = b / p.npix - mean * mean;
+                        if (var < 0) var = 0;
+                        p.norm[t] = (float)mean;
+                        p.norm[128 + t] = (float)((double)p.gamma[t] / sqrt(var + 1e-5));
+                    }
+                    if (t == 0) *p.ticket = 0;
+                }
             }
         }
     }
@@ -536,7 +618,7 @@ int launch_cl(dmp2_engine* e, int cl, const ConvMaps& maps, const TcParams& p, i
 // xh/xl/x8lo/x8hi: activation maps of map_rows x L pixels; output row y reads map rows y + y_off - 2 .. y + y_off + 2
 // (rows outside the map read as zero), H output rows are written to raw.  Whole image: map_rows = H = L, y_off = 0.
 int run_conv_tc(dmp2_engine* e, int blk, const __half* xh, const __half* xl, const uint8_t* x8lo, const uint8_t* x8hi, int L,
-                int H, int y_off, int map_rows, float* raw, int mode, cudaStream_t st) {
+                int H, int y_off, int map_rows, float* raw, int mode, cudaStream_t st, bool fuse_stats) {
     TcState* s;
     TRY(get_state(e, &s));
     const ResBlockW& bw = e->w.blk[blk];
@@ -564,9 +646,19 @@ int run_conv_tc(dmp2_engine* e, int blk, const __half* xh, const __half* xl, con
     p.gemm = 0; p.L = L; p.H = H; p.y_off = y_off; p.tiles_x = cdiv(L, TILE_W); p.num_kb = 50; p.M = H * L; p.out = raw; p.bias = bw.bias;
     const int grid = p.tiles_x * cdiv(H, TILE_H);
     const int cl = e->conv_cluster;
+    p.stat_part = nullptr; p.ticket = nullptr; p.norm = nullptr; p.gamma = nullptr; p.totals = nullptr; p.npix = 0;
+    if (fuse_stats && cl != 0) {                     // (the CTA-pair kernel keeps the separate statistics pass)
+        p.stat_part = e->ws.stat_part; p.ticket = e->ws.ticket; p.norm = e->ws.norm_ss; p.gamma = bw.gamma;
+        p.totals = e->strip_on ? e->sp.totals : nullptr;
+        p.npix = (double)H * (double)L;
+    }
     if (mode == DMP2_CONV_TC_F16X3) return launch_cl<M_F16X3>(e, cl, maps, p, grid, st);
     if (mode == DMP2_CONV_TC_F16F8) return launch_cl<M_F16F8>(e, cl, maps, p, grid, st);
     return launch_cl<M_F16>(e, cl, maps, p, grid, st);
+}
+
+bool conv_tc_fuses_stats(const dmp2_engine* e) {
+    return e->fuse_stats && e->conv_mode != DMP2_CONV_FFMA && e->conv_cluster != 0;
 }
 
 // C[M,512] = A[M,K] * B[512,K]^T through the same TMA / tcgen05 / TMEM pipeline (descriptor + pipeline self-test)
@@ -593,7 +685,7 @@ int run_gemm_tn_test(dmp2_engine* e, const float* a, const float* b, int M, int 
         if ((rc = weight_map(e, &maps.b_lo, bl, K, 2))) break;
         maps.a8_lo = maps.a_hi; maps.a8_hi = maps.a_hi; maps.b8_w = maps.b_hi; maps.b8_lo = maps.b_hi;    // unused in these modes
         TcParams p;
-        p.gemm = 1; p.L = 0; p.H = 0; p.y_off = 0; p.tiles_x = 1; p.num_kb = K / KCHUNK; p.M = M; p.out = c; p.bias = nullptr;
+        p.gemm = 1; p.L = 0; p.H = 0; p.y_off = 0; p.stat_part = nullptr; p.ticket = nullptr; p.norm = nullptr; p.gamma = nullptr; p.totals = nullptr; p.npix = 0; p.tiles_x = 1; p.num_kb = K / KCHUNK; p.M = M; p.out = c; p.bias = nullptr;
         int grid = cdiv(M, TILE_M);
         rc = (mode == DMP2_CONV_TC_F16X3) ? launch<M_F16X3, 1>(e, maps, p, grid, st) : launch<M_F16, 1>(e, maps, p, grid, st);
     } while (0);

@@ -275,10 +275,14 @@ int ensure_workspace(dmp2_engine* e, int L, int N, int rows2d) {
     TRY(wsalloc(e, &ws.xl, PA * 128));
     TRY(wsalloc(e, &ws.x8lo, PA * 128));
     TRY(wsalloc(e, &ws.x8hi, PA * 128));
-    TRY(wsalloc(e, &ws.stat_part, (int64_t)e->num_sms * 4 * 256));
+    // InstanceNorm partial sums: one row per k_in_stats CTA, or per conv tile (+ its cluster padding) when the conv
+    // epilogue produces them, plus the first-level fold results
+    const int64_t stat_ctas = std::max<int64_t>((int64_t)e->num_sms * 2, (int64_t)cdiv(L, 16) * cdiv(rows2d, 8) + 4);
+    const int64_t stat_grps = stat_ctas / 16 + 2;
+    TRY(wsalloc(e, &ws.stat_part, (stat_ctas + stat_grps) * 256));
     TRY(wsalloc(e, &ws.norm_ss, 256));
-    TRY(wsalloc(e, &ws.ticket, 64));
-    CUDA_TRY(e, cudaMemset(ws.ticket, 0, 64 * sizeof(unsigned int)));
+    TRY(wsalloc(e, &ws.ticket, 64 + stat_grps));
+    CUDA_TRY(e, cudaMemset(ws.ticket, 0, (64 + stat_grps) * sizeof(unsigned int)));
     TRY(wsalloc(e, &ws.head, 2 * P));
     TRY(wsalloc(e, &ws.conf, L));
     TRY(wsalloc(e, &ws.mmat, P));
@@ -423,6 +427,8 @@ int dmp2_create(dmp2_engine** out, int device, int n_tensors, const char* const*
     if (cc && (!strcmp(cc, "1") || !strcmp(cc, "2") || !strcmp(cc, "4"))) e->conv_cluster = atoi(cc);
     if (cc && !strcmp(cc, "pair")) e->conv_cluster = 0;        // cta_group::2 CTA-pair kernel
     const char* vm = getenv("DMP2_VGRU");
+    const char* fs = getenv("DMP2_FUSE_STATS");
+    if (fs) e->fuse_stats = strcmp(fs, "0") != 0;
     if (vm && !strcmp(vm, "ffma")) e->vgru_mode = 1;
     if (vm && !strcmp(vm, "persist")) e->vgru_mode = 2;
     if (vm && !strcmp(vm, "steps")) e->vgru_mode = 0;

@@ -224,15 +224,17 @@ int run_stem_update(dmp2_engine* e, const float* dmap, int L, cudaStream_t st) {
     return run_norm_gate(e, -1, ws.raw, ws.x, L, true, st);
 }
 
-int run_norm_gate(dmp2_engine* e, int blk, const float* raw, float* x, int L, bool stem, cudaStream_t st) {
+int run_norm_gate(dmp2_engine* e, int blk, const float* raw, float* x, int L, bool stem, cudaStream_t st, bool have_stats) {
     Workspace& ws = e->ws;
     const Rows rw = rows_of(e, L);
     const int64_t npix = (int64_t)rw.R * L;
     const float* gamma = stem ? e->w.stem_gamma : e->w.blk[blk].gamma;
     const float* beta = stem ? e->w.stem_beta : e->w.blk[blk].beta;
-    int sgrid = (int)std::min<int64_t>(cdiv64(npix, 64), (int64_t)e->num_sms * 2);
-    k_in_stats<<<sgrid, 512, 0, st>>>(raw, npix, gamma, ws.stat_part, ws.ticket, ws.norm_ss, e->strip_on ? e->sp.totals : nullptr);
-    POST_LAUNCH(e, "k_in_stats");
+    if (!have_stats) {                                   // (after a tensor-core conv the sums come from its epilogue)
+        int sgrid = (int)std::min<int64_t>(cdiv64(npix, 64), (int64_t)e->num_sms * 2);
+        k_in_stats<<<sgrid, 512, 0, st>>>(raw, npix, gamma, ws.stat_part, ws.ticket, ws.norm_ss, e->strip_on ? e->sp.totals : nullptr);
+        POST_LAUNCH(e, "k_in_stats");
+    }
     if (e->strip_on) TRY(strip_stats_exchange(e, gamma, ws.norm_ss, st));      // statistics are over ALL rows of the map
     const ActPtrs act = act_of(e, L);
     int agrid = (int)std::min<int64_t>(cdiv64(npix, 8), (int64_t)e->num_sms * 8);
@@ -280,6 +282,7 @@ int run_conv_ffma(dmp2_engine* e, int blk, const float* x, int L, float* raw, cu
 int run_resblock(dmp2_engine* e, int blk, int L, cudaStream_t st) {
     Workspace& ws = e->ws;
     const bool prof = e->profile && e->prof_used + 2 <= e->prof_ev.size();
+    const bool fused = conv_tc_fuses_stats(e);
     if (prof) cudaEventRecord(e->prof_ev[e->prof_used], st);
     if (e->strip_on) {
         // strip of R rows; the activation copies carry 2 halo rows on each side, filled by the neighbours
@@ -287,11 +290,11 @@ int run_resblock(dmp2_engine* e, int blk, int L, cudaStream_t st) {
         const StripCtx& sp = e->sp;
         TRY(strip_halo_wait(e, st));
         TRY(run_conv_tc(e, blk, reinterpret_cast<const __half*>(sp.win + sp.off_act[0]), reinterpret_cast<const __half*>(sp.win + sp.off_act[1]),
-                        sp.win + sp.off_act[2], sp.win + sp.off_act[3], L, rw.R, 2, rw.R + 4, ws.raw, e->conv_mode, st));
+                        sp.win + sp.off_act[2], sp.win + sp.off_act[3], L, rw.R, 2, rw.R + 4, ws.raw, e->conv_mode, st, fused));
     } else if (e->conv_mode == DMP2_CONV_FFMA) TRY(run_conv_ffma(e, blk, ws.x, L, ws.raw, st));
-    else TRY(run_conv_tc(e, blk, ws.xh, ws.xl, ws.x8lo, ws.x8hi, L, L, 0, L, ws.raw, e->conv_mode, st));
+    else TRY(run_conv_tc(e, blk, ws.xh, ws.xl, ws.x8lo, ws.x8hi, L, L, 0, L, ws.raw, e->conv_mode, st, fused));
     if (prof) { cudaEventRecord(e->prof_ev[e->prof_used + 1], st); e->prof_used += 2; }
-    return run_norm_gate(e, blk, ws.raw, ws.x, L, false, st);
+    return run_norm_gate(e, blk, ws.raw, ws.x, L, false, st, fused && e->conv_mode != DMP2_CONV_FFMA);
 }
 
 // ---------------------------------------------------------------------------------------------------

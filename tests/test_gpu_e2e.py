@@ -187,3 +187,22 @@ def test_batch_api(pf10963, tmp_path):
     assert len(res) == 2 and res[0][0].shape == (82, 5, 3) and res[1][0].shape == (40, 5, 3)
     c, f = aln_to_coords(str(short), device='cuda:0', iterations=1, minsteps=5)
     assert torch.equal(res[1][0], c.cpu()) and torch.equal(res[1][1], f.cpu())
+
+
+@needs_weights
+def test_fused_stats_variant(state_dict, pf10963, monkeypatch):
+    """DMP2_FUSE_STATS=1: the InstanceNorm sums come out of the conv epilogue instead of k_in_stats.  Same statistics
+    up to the fp64 summation order, so the fold must agree with the default path far below the parity tolerance."""
+    from dmpfold2_b200.engine import Engine
+    from dmpfold2_b200.synth import synth_msa_structured
+    msa = synth_msa_structured(pf10963, 150, 64, 5)
+    e0 = Engine(state_dict, 0)
+    c0, f0 = e0.fold_host(msa, None, 2, 20)
+    e0.close()
+    monkeypatch.setenv('DMP2_FUSE_STATS', '1')
+    e1 = Engine(state_dict, 0)
+    c1, f1 = e1.fold_host(msa, None, 2, 20)
+    n_fused = e1.launch_count
+    e1.close()
+    assert O.kabsch_rmsd(c1[:, 1], c0[:, 1]) < 1e-5 and np.abs(f1 - f0).max() < 1e-5
+    assert np.isfinite(c1).all() and n_fused > 0
