@@ -2,8 +2,9 @@
 // Direct method, fp64 internally (the spectrum is hostile to iterative schemes: strongly indefinite,
 // lambda_9/lambda_8 up to 0.996 -- SURVEY.md section 7.2):
 //   1. Householder tridiagonalisation, rows distributed cyclically over an 8-CTA cluster (resident in shared
-//      memory when they fit), the Householder vector / matrix-vector product all-gathered through distributed
-//      shared memory, two cluster barriers per column;
+//      memory when they fit); rank-2 update and next matrix-vector product fused into one sweep, ONE all-gather
+//      per column through distributed shared memory (st.async + mbarrier, no cluster barrier in the loop);
+//      beyond the cluster's capacity the same fused scheme runs on the whole GPU (k_tridiag_grid);
 //   2. Sturm multi-section (32 shifts per round) for the 8 largest eigenvalues      } CTA 0
 //   3. inverse iteration + Gram-Schmidt, 4. back-transformation                      }
 //   5. canonical sign (largest-|component| positive, lowest index wins ties), sqrt(clamp(relu(l),1e-8)) scaling.
@@ -85,8 +86,7 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
     cg::cluster_group cluster = cg::this_cluster();
     const int c = (int)cluster.block_rank();
     extern __shared__ double sm[];
-    double* svb = sm;                // [2][n] householder vector (ping-pong)
-    double* spb = sm + 2 * n;        // [2][n] p, then w          (ping-pong)
+    // [0, 7n): Householder work vectors during phase 1 (see there); afterwards
     double* sd = sm + 4 * n;         // [n] diagonal of T
     double* se = sm + 5 * n;         // [n] off-diagonal of T
     double* se2 = sm + 6 * n;        // [n] e^2
@@ -123,99 +123,120 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
         double* dst = rbase + li * rstride;
         for (int j = lane; j < n; j += 32) dst[j] = (double)src[j];
     }
-    cluster.sync();
 
     // ---------------- 1. Householder tridiagonalisation ----------------------------------------------------
-    // Per column two all-gathers across the cluster (the column itself, then A v).  Every value travels as an
-    // st.async store that complete_tx's on the destination CTA's mbarrier, so there is no cluster-wide barrier in
-    // the loop: a CTA waits only until its own copy of the gathered vector is complete.  Buffers and barriers are
-    // ping-ponged by column parity; a CTA can run at most one gather ahead of its slowest peer.
-    // The first component of the Householder vector (v0) is carried in a register, the gathered column is never
-    // patched.
-    __shared__ __align__(8) unsigned long long gbar[4];          // [column gather | p gather][parity]
+    // Fused form: iteration k applies the rank-2 update of column k (v, w) to the owned rows and, in the same sweep,
+    // multiplies them with the NEXT Householder vector v' -- which every CTA can form on its own, because the raw
+    // entries of the next column were all-gathered one iteration earlier and the pending update of that column only
+    // needs v and w.  So there is ONE all-gather per column, carrying two doubles per row: p'_i = (A v')_i and the
+    // row's freshly updated entry of the column after next.  Every value travels as an st.async store that
+    // complete_tx's on the destination CTA's mbarrier: no cluster-wide barrier in the loop, a CTA waits only until its
+    // own copy is complete.  Buffers and barriers are ping-ponged by column parity; a CTA can run at most one gather
+    // ahead of its slowest peer.  Shared memory (7 n doubles, the d/e/e^2 arrays alias the tail):
+    double* sv = sm;                 // [n] v of the column being applied (index = row - c0), v[0] = v0
+    double* sw = sm + n;             // [n] w = p - kk v
+    double* sv2 = sm + 2 * n;        // [n] next Householder vector (entry 0 is kept in a register: v0n)
+    double* pgb = sm + 3 * n;        // [2][n] gathered p'
+    double* xgb = sm + 5 * n;        // [2][n] gathered raw next column
+    __shared__ __align__(8) unsigned long long gbar[2];
     const uint32_t gbar0 = cc::smem_u32(&gbar[0]);
     if (tid == 0) {
-        for (int i = 0; i < 4; i++) cc::bar_init(gbar0 + 8 * i, 1);
+        cc::bar_init(gbar0, 1);
+        cc::bar_init(gbar0 + 8, 1);
         cc::bar_init_fence();
     }
-    const uint32_t sp_a = cc::smem_u32(spb);
-    uint32_t peer_sv[EIG_CL], peer_bar[EIG_CL];                   // peers' svb / gbar base addresses
-#pragma unroll
-    for (int d = 0; d < EIG_CL; d++) {
-        peer_sv[d] = cc::mapa(cc::smem_u32(svb), d);
-        peer_bar[d] = cc::mapa(gbar0, d);
+    for (int j = tid; j < n; j += EIG_THREADS) {
+        sv[j] = 0.0; sw[j] = 0.0;
+        xgb[j] = (double)M[(int64_t)j * n];                       // raw column 0 (parity 0 buffer)
     }
+    const uint32_t pg_a = cc::smem_u32(pgb), xg_a = cc::smem_u32(xgb);
     cluster.sync();
-    uint32_t gph = 0;                                             // phase parity bits of the four barriers
-    for (int k = 0; k < n - 2; k++) {
-        const int m = n - k - 1;                       // length of the column below the diagonal
-        const int pp = k & 1;
-        double* sv = svb + pp * n;
-        double* sp = spb + pp * n;
-        const uint32_t bar_col = gbar0 + 8 * pp, bar_p = gbar0 + 8 * (2 + pp);
-        const int li0 = (k + 1 - c + EIG_CL - 1) / EIG_CL;           // first local row with global index > k
-        if (tid == 0) { cc::bar_expect_tx(bar_col, (uint32_t)m * 8u); cc::bar_expect_tx(bar_p, (uint32_t)m * 8u); }
-        for (int li = li0 + tid; li < nloc; li += EIG_THREADS) {
-            const int i = li * EIG_CL + c;
-            const double x = rbase[li * rstride + k];
-            const uint32_t off = (uint32_t)(pp * n + i - k - 1) * 8u;
-#pragma unroll
-            for (int d = 0; d < EIG_CL; d++) cc::st_async_f64(peer_sv[d] + off, x, peer_bar[d] + 8 * pp);
-        }
-        if (tid == 0 && (k % EIG_CL) == c) gd[k] = rbase[(k / EIG_CL) * rstride + k];
-        cc::bar_wait(bar_col, (gph >> pp) & 1u);
-        gph ^= 1u << pp;
+    uint32_t gph = 0;                                             // phase parity bits of the two barriers
+    for (int k = -1; k <= n - 3; k++) {
+        const int c0 = k + 1;                          // first row / column of the trailing matrix
+        const int m = n - c0;
+        const int par = c0 & 1;                        // buffers read in this iteration; the gather fills par ^ 1
+        const double* xcol = xgb + par * n;            // raw column c0, rows c0.. (index = row - c0)
+        const bool last = (k == n - 3);
+        if (tid == 0 && !last) cc::bar_expect_tx(gbar0 + 8 * (par ^ 1), (uint32_t)(m - 1) * 16u);
+        // ---- A. finish column c0 locally: r = raw - (v w[0] + w v[0]);  d = r[0];  x = r[1..) -> next Householder vector
+        const double v_0 = sv[0], w_0 = sw[0];
         double part = 0.0;
-        for (int i = tid; i < m; i += EIG_THREADS) part += sv[i] * sv[i];
+        for (int j = tid; j < m; j += EIG_THREADS) {
+            const double r = xcol[j] - (sv[j] * w_0 + sw[j] * v_0);
+            if (j == 0) { if (c == 0) gd[c0] = r; }
+            else { sv2[j - 1] = r; part += r * r; }
+        }
         const double sigma = block_sum1(part, scr_a);
-        const double x0 = sv[0];
-        const double tail = sigma - x0 * x0;
-        const bool reflect = tail > 0.0;               // false: column already tridiagonal, H = I
-        const double alpha = reflect ? ((x0 >= 0.0) ? -sqrt(sigma) : sqrt(sigma)) : x0;
-        const double v0 = x0 - alpha;
-        const double bt = reflect ? 2.0 / (tail + v0 * v0) : 0.0;
-        if (c == 0) {
-            if (tid == 0) { ge[k] = alpha; beta[k] = bt; }
-            for (int i = tid; i < m; i += EIG_THREADS) V[(int64_t)k * n + i] = i == 0 ? v0 : sv[i];
+        double bt2 = 0.0, v0n = 0.0;
+        if (m >= 3) {
+            const double x0 = sv2[0];
+            const double tail = sigma - x0 * x0;
+            const bool reflect = tail > 0.0;               // false: column already tridiagonal, H = I
+            const double alpha = reflect ? ((x0 >= 0.0) ? -sqrt(sigma) : sqrt(sigma)) : x0;
+            v0n = x0 - alpha;
+            bt2 = reflect ? 2.0 / (tail + v0n * v0n) : 0.0;
+            if (c == 0) {
+                if (tid == 0) { ge[c0] = alpha; beta[c0] = bt2; }
+                for (int j = tid; j < m - 1; j += EIG_THREADS) V[(int64_t)c0 * n + j] = j == 0 ? v0n : sv2[j];
+            }
+        } else if (c == 0 && tid == 0) {                    // last 2 x 2 block: no reflector left
+            ge[c0] = sv2[0];
+            ge[n - 1] = 0.0;
         }
-        // p = beta * A22 v for the rows this CTA owns, all-gathered into every CTA's sp
+        // ---- B. one sweep over the owned rows i > c0: update with (v, w), dot with v', all-gather (p'_i, A[i][c0+1])
+        const int li0 = (c0 + 1 - c + EIG_CL - 1) / EIG_CL;           // first local row with global index > c0
         for (int li = li0 + warp; li < nloc; li += NW) {
-            const double* row = rbase + li * rstride + (k + 1);
-            double acc = lane == 0 ? row[0] * v0 : 0.0, acc2 = 0.0;
-            int j = lane == 0 ? 32 : lane;
-#pragma unroll 4
-            for (; j + 32 < m; j += 64) { acc += row[j] * sv[j]; acc2 += row[j + 32] * sv[j + 32]; }
-            if (j < m) acc += row[j] * sv[j];
-            acc = warp_sum(acc + acc2) * bt;
-            if (lane < EIG_CL)
-                cc::st_async_f64(cc::mapa(sp_a, lane) + (uint32_t)(pp * n + li * EIG_CL + c - k - 1) * 8u, acc,
-                                 cc::mapa(gbar0, lane) + 8 * (2 + pp));
-        }
-        cc::bar_wait(bar_p, (gph >> (2 + pp)) & 1u);
-        gph ^= 1u << (2 + pp);
-        double pv = 0.0;
-        for (int i = tid; i < m; i += EIG_THREADS) pv += sp[i] * (i == 0 ? v0 : sv[i]);
-        const double kk = 0.5 * bt * block_sum1(pv, scr_b);
-        // rank-2 update of the owned rows with w = p - kk v formed on the fly (bt == 0 -> p == 0 -> no change)
-        if (reflect) {
-            for (int li = li0 + warp; li < nloc; li += NW) {
-                double* row = rbase + li * rstride + (k + 1);
-                const int i = li * EIG_CL + c - k - 1;
-                const double vi = i == 0 ? v0 : sv[i];
-                const double wi = sp[i] - kk * vi;
-#pragma unroll 8
-                for (int j = lane; j < m; j += 32) {
-                    const double vj = j == 0 ? v0 : sv[j];
-                    row[j] -= vi * (sp[j] - kk * vj) + wi * vj;
-                }
+            const int i = li * EIG_CL + c, ti = i - c0;
+            double* row = rbase + li * rstride + c0;
+            const double vi = sv[ti], wi = sw[ti];
+            double acc = 0.0, acc2 = 0.0, xn = 0.0;
+            int j = 1 + lane;
+            if (j < m) {                                   // first chunk: column c0+1 is the one gathered for the next step
+                const double a = row[j] - (vi * sw[j] + wi * sv[j]);
+                row[j] = a;
+                acc = a * (j == 1 ? v0n : sv2[j - 1]);
+                xn = a;
+                j += 32;
+            }
+#pragma unroll 2
+            for (; j + 32 < m; j += 64) {
+                const double a = row[j] - (vi * sw[j] + wi * sv[j]);
+                const double b = row[j + 32] - (vi * sw[j + 32] + wi * sv[j + 32]);
+                row[j] = a; row[j + 32] = b;
+                acc += a * sv2[j - 1];
+                acc2 += b * sv2[j + 31];
+            }
+            if (j < m) {
+                const double a = row[j] - (vi * sw[j] + wi * sv[j]);
+                row[j] = a;
+                acc += a * sv2[j - 1];
+            }
+            acc = warp_sum(acc + acc2) * bt2;
+            xn = __shfl_sync(0xffffffffu, xn, 0);
+            if (last) {
+                if (lane == 0 && i == n - 1) gd[n - 1] = xn;
+            } else if (lane < EIG_CL) {
+                const uint32_t off = (uint32_t)((par ^ 1) * n + ti - 1) * 8u;
+                const uint32_t pbar = cc::mapa(gbar0, lane) + 8 * (par ^ 1);
+                cc::st_async_f64(cc::mapa(pg_a, lane) + off, acc, pbar);
+                cc::st_async_f64(cc::mapa(xg_a, lane) + off, xn, pbar);
             }
         }
+        if (last) break;
+        // ---- C. gathered p' -> w' = p' - kk' v';  v <- v'
+        cc::bar_wait(gbar0 + 8 * (par ^ 1), (gph >> (par ^ 1)) & 1u);
+        gph ^= 1u << (par ^ 1);
+        const double* pg = pgb + (par ^ 1) * n;
+        double pv = 0.0;
+        for (int j = tid; j < m - 1; j += EIG_THREADS) pv += pg[j] * (j == 0 ? v0n : sv2[j]);
+        const double kk = 0.5 * bt2 * block_sum1(pv, scr_b);
+        for (int j = tid; j < m - 1; j += EIG_THREADS) {
+            const double vj = j == 0 ? v0n : sv2[j];
+            sv[j] = vj;
+            sw[j] = pg[j] - kk * vj;
+        }
         __syncthreads();
-    }
-    if (tid == 0) {
-        for (int i = n - 2; i < n; i++)
-            if (i >= 0 && (i % EIG_CL) == c) gd[i] = rbase[(i / EIG_CL) * rstride + i];
-        if (((n - 1) % EIG_CL) == c) { ge[n - 2] = rbase[((n - 1) / EIG_CL) * rstride + (n - 2)]; ge[n - 1] = 0.0; }
     }
     __threadfence();
     cluster.sync();
