@@ -176,3 +176,25 @@ def test_strip_partition_is_pure_host_arithmetic():
         strip_rows(300, 9, 0)
     with pytest.raises(ValueError):
         strip_rows(300, 4, 4)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference: the CPU arm the driver times next to the engine -- one JSON line with the keys of the
+    bench contract, `impl` = reference, an e2e block that repeats its own value, no GPU needed."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0'],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines                                      # ONE line on stdout
+    d = json.loads(lines[0])
+    for k in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling', 'vs_baseline',
+              'dtype', 'data', 'config', 'e2e', 'cpu_baseline', 'impl'):
+        assert k in d, k
+    assert d['impl'] == 'reference' and d['unit'] == 'ms/target' and d['higher_is_better'] is False and d['vs_baseline'] is None
+    assert 'workload' in d['config'] and 'L=300' in d['metric']
+    assert d['e2e'] == {'value': d['value'], 'unit': 'ms/target', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] == os.cpu_count() and d['cpu_baseline']['value'] == d['value']
+    assert d['value'] > 1000.0                                         # seconds, not milliseconds, per target on CPU
