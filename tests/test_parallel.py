@@ -62,3 +62,59 @@ def test_two_rank_gloo_fold_many(tmp_path):
     port = _free_port()
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert os.path.isfile(tmp_path / 'ok0') and os.path.isfile(tmp_path / 'ok1')
+
+
+class _FakeEngine:
+    """Records the strip calls a StripGroup makes (the real ones need a GPU): same method names and return shapes."""
+
+    def __init__(self, rank):
+        self.rank, self.calls, self.device = rank, [], torch.device('cpu')
+
+    def strip_setup(self, rank, world, l, reserve_n=0):
+        self.calls.append(('setup', rank, world, l, reserve_n))
+        return bytes([rank + 1]) * 64, 1000 + rank
+
+    def strip_attach(self, handles):
+        self.calls.append(('attach', tuple(handles)))
+
+    def strip_detach(self):
+        self.calls.append(('detach',))
+
+    def fold_strip_host(self, msa, tmpl, n, m):
+        self.calls.append(('fold', msa.shape, n, m))
+        return 'coords', 'confs'
+
+
+def _strip_worker(rank, world_size, port, out_dir):
+    import numpy as np
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world_size)
+    try:
+        real_sync = torch.cuda.synchronize
+        torch.cuda.synchronize = lambda *a, **k: None          # no device in the CPU suite
+        eng = _FakeEngine(rank)
+        grp = P.StripGroup(eng)
+        assert (grp.rank, grp.world) == (rank, world_size)
+        both = tuple(bytes([r + 1]) * 64 for r in range(world_size))
+        assert grp.fold_host(np.zeros((7, 100), np.uint8), None, 1, 2) == ('coords', 'confs')
+        grp.fold_host(np.zeros((9, 100), np.uint8), None, 0, 0)            # same length: the windows are reused
+        grp.fold_host(np.zeros((5, 120), np.uint8), None, 0, 0)            # new length: collective re-setup
+        grp.close()
+        grp.close()                                                        # idempotent
+        torch.cuda.synchronize = real_sync
+        assert eng.calls == [
+            ('setup', rank, world_size, 100, 7), ('attach', both), ('fold', (7, 100), 1, 2), ('fold', (9, 100), 0, 0),
+            ('detach',), ('setup', rank, world_size, 120, 5), ('attach', both), ('fold', (5, 120), 0, 0), ('detach',)], eng.calls
+        with open(os.path.join(out_dir, f'strip_ok{rank}'), 'w') as fh:
+            fh.write('ok')
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_strip_group_host_logic(tmp_path):
+    """StripGroup: one-off exchange of the window handles in rank order, windows re-made only when L changes,
+    detach bracketed by barriers -- checked with two gloo ranks and a recording stand-in for the engine."""
+    port = _free_port()
+    mp.spawn(_strip_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert sorted(os.listdir(tmp_path)) == ['strip_ok0', 'strip_ok1']
