@@ -198,3 +198,14 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d['e2e'] == {'value': d['value'], 'unit': 'ms/target', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] == os.cpu_count() and d['cpu_baseline']['value'] == d['value']
     assert d['value'] > 1000.0                                         # seconds, not milliseconds, per target on CPU
+
+
+def test_packaging_metadata():
+    """setup.py mirrors the reference's packaging surface (setup.py:6-25 there): a package + the `dmpfold` script."""
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, 'setup.py', '--name', '--version'], cwd=ROOT, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr[-1000:]
+    assert out.stdout.split()[-2:] == ['dmpfold2-b200', '0.1']
+    src = open(os.path.join(ROOT, 'setup.py')).read()
+    assert "scripts=['bin/dmpfold']" in src and 'libdmp2.so' in src and os.access(os.path.join(ROOT, 'bin', 'dmpfold'), os.X_OK)
