@@ -8,6 +8,8 @@ f16f8: would block-scaled FP4 correction terms (tcgen05 kind::mxf4, 2x the fp8 r
   f16x3       + x_lo * w_hi + x_hi * w_lo   (fp16 operands)
   f16f8       + e4m3(x_lo 2^8) e5m2(w 2^-8) + e4m3(x_hi 2^-4) e5m2(w_lo 2^4)      (what the engine runs)
   f16f4       + mxfp4(x_lo) mxfp4(w) + mxfp4(x_hi) mxfp4(w_lo)                    (e2m1, one power-of-two scale per 32 K-elements)
+  f16nv4      same with NVFP4 operands (e2m1, one e4m3 scale per 16 K-elements)
+  f16f4/8     mxfp4 for the x_lo term only, the engine's fp8 operands for the w_lo term
 """
 import os
 import sys
@@ -52,6 +54,21 @@ def q_mxfp4(t, dim):
     return q.reshape(shp).movedim(-1, dim)
 
 
+def q_nvfp4(t, dim):
+    """e2m1 with one e4m3 scale per 16 consecutive elements along `dim` (NVFP4; a per-tensor fp32 scale keeps the e4m3
+    scales in range, modelled here by normalising with the tensor's amax first)."""
+    g = t.abs().max().clamp_min(1e-300)
+    t = (t / g).movedim(dim, -1)
+    shp = t.shape
+    b = t.reshape(-1, 16)
+    sc = (b.abs().amax(dim=1, keepdim=True) / 6.0 * 448.0).to(torch.float32).to(torch.float8_e4m3fn).to(torch.float64) / 448.0
+    sc = sc.clamp_min(1e-300)
+    v = (b / sc).clamp(-6.0, 6.0)
+    idx = (v.abs().unsqueeze(-1) - E2M1).abs().argmin(dim=-1)
+    q = E2M1[idx] * v.sign() * sc
+    return (q.reshape(shp).movedim(-1, dim)) * g
+
+
 def conv(xq, wq):
     return F.conv2d(xq, wq, None, padding=2)
 
@@ -70,6 +87,7 @@ for blk, key in ((1, 'stem'), (9, 'block8'), (16, 'block15')):
                           + conv(q_f8(xh, torch.float8_e4m3fn, 1 / 16.0), q_f8(wl, torch.float8_e5m2, 16.0)),
             # K runs over (tap, channel) with the 128 channels contiguous -> blocks of 32 channels (dim 1) for both operands
             'f16f4': main + conv(q_mxfp4(xl, 1), q_mxfp4(w, 1)) + conv(q_mxfp4(xh, 1), q_mxfp4(wl, 1)),
+            'f16nv4': main + conv(q_nvfp4(xl, 1), q_nvfp4(w, 1)) + conv(q_nvfp4(xh, 1), q_nvfp4(wl, 1)),
             'f16f4/8': main + conv(q_mxfp4(xl, 1), q_mxfp4(w, 1)) + conv(q_f8(xh, torch.float8_e4m3fn, 1 / 16.0), q_f8(wl, torch.float8_e5m2, 16.0)),
             }
     print(f'block {blk}: |out|max {float(scale):.1f}', flush=True)
