@@ -133,5 +133,32 @@ def main():
         print('single mean conf', float(f.mean()))
 
 
+def synthetic_golden():
+    """A second pin at another size: the structured synthetic alignment the halo-sharded tests use (L=100, N=96,
+    seed 3), written out as an .aln file and folded by the reference (n=2, m=20)."""
+    install_shim()
+    sys.path.insert(0, REF)
+    sys.path.insert(0, os.path.join(HERE, '..'))
+    import dmpfold
+    from oracle import dmpfold_oracle as O
+    torch.set_num_threads(8)
+    base = O.encode_aln(O.read_aln(os.path.join(REF, 'dmpfold', 'example', 'PF10963.aln')))
+    msa = O.synth_msa_structured(base, 100, 96, 3)
+    letters = 'ARNDCQEGHILKMFPSTWYVX-'                      # codes 0..19, 20 = unknown, 21 = gap (predict.py:124-128)
+    with tempfile.TemporaryDirectory() as td:
+        aln = os.path.join(td, 'synth.aln')
+        with open(aln, 'w') as fh:
+            for row in msa:
+                fh.write(''.join(letters[c] for c in row) + '\n')
+        c, f, alnmat = dmpfold.aln_to_coords(aln, iterations=2, minsteps=20, return_alnmat=True)
+    assert np.array_equal(alnmat, msa), 'the .aln round trip must reproduce the synthetic codes'
+    np.savez_compressed(os.path.join(GOLD, 'synth_l100_n96_s3_n2_m20.npz'), msa=msa, coords=c.numpy(), confs=f.numpy())
+    print('synthetic L=100 N=96 n2m20 mean conf', float(f.mean()))
+
+
 if __name__ == '__main__':
-    main()
+    if '--synthetic' in sys.argv:
+        synthetic_golden()                                   # python oracle/make_golden.py --synthetic
+    else:
+        main()
+        synthetic_golden()

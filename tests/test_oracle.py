@@ -57,6 +57,22 @@ def test_forward_n2_m20_matches_reference(oracle, pf10963):
 
 
 @needs_weights
+def test_forward_synthetic_l100_matches_reference(oracle, pf10963):
+    """Second pin at another size: the structured synthetic alignment of the halo-sharded tests, folded by the
+    reference itself (oracle/make_golden.py --synthetic).  Also pins the generator: oracle copy == product copy == the
+    codes the reference parsed back from the .aln text."""
+    from dmpfold2_b200.synth import synth_msa_structured
+    g = _gold('synth_l100_n96_s3_n2_m20.npz')
+    msa = O.synth_msa_structured(pf10963, 100, 96, 3)
+    assert np.array_equal(msa, g['msa']) and np.array_equal(synth_msa_structured(pf10963, 100, 96, 3), g['msa'])
+    coords, conf = oracle.fold(msa, iterations=2, minsteps=20)
+    rmsd = O.kabsch_rmsd(coords[:, 1].numpy(), g['coords'][:, 1])
+    print(f'oracle vs reference on the synthetic L=100 target: CA-RMSD {rmsd:.2e} A')
+    assert rmsd < 2e-4
+    np.testing.assert_allclose(conf.numpy(), g['confs'], atol=1e-4)
+
+
+@needs_weights
 def test_template_and_single_sequence_match_reference(oracle, pf10963, tmp_path):
     g = _gold('pf10963_tmpl_n1_m10.npz')
     pdb = tmp_path / 'tmpl.pdb'
