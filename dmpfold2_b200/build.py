@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OBJ = os.path.join(HERE, 'build')
 LIB = os.path.join(HERE, 'libdmp2.so')
-SOURCES = ['engine.cu', 'msa.cu', 'gru.cu', 'resnet.cu', 'conv_tc.cu', 'vgru_tc.cu', 'vgru_persist.cu', 'eig.cu', 'geom.cu', 'strip.cu']
+SOURCES = ['engine.cu', 'msa.cu', 'gru.cu', 'resnet.cu', 'conv_tc.cu', 'vgru_tc.cu', 'eig.cu', 'geom.cu', 'strip.cu']
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-Xcompiler', '-fPIC',
          '--expt-relaxed-constexpr', '-Xptxas', '-v']

@@ -126,10 +126,6 @@ struct Workspace {
     float* vg_h = nullptr;         // [2 layers][2 buffers][L][512]
     __half* vt_h16 = nullptr;      // [4 buffers][hi|lo][L][512] fp16 split of the vgru states
     float* vt_gi1 = nullptr;       // [2][L][1536] layer-1 input projections in flight
-    __half* vp_h16 = nullptr;      // persistent vgru: [h0_hi 4][h0_lo 4][h1_hi 2][h1_lo 2] x [L][512]
-    float* vp_f32 = nullptr;       // persistent vgru: [h0 4][h1 2] x [L][512]
-    float* vp_gi1 = nullptr;       // persistent vgru: [4][L][1536]
-    unsigned int* vp_cnt = nullptr; // persistent vgru: [row tiles][3] progress counters
     float* v_last = nullptr;       // [L][512]
     float* gi = nullptr;           // [L][1536] input projections of the current bi-GRU layer
     float* seq_a = nullptr;        // [L][520] layer input / output ping
@@ -161,6 +157,7 @@ struct Workspace {
     float* coords_out = nullptr;   // [L][5][3]
     float* conf_out = nullptr;     // [L]
     int rows2d = 0;                // rows of the 2-D track held here (L, or a strip height in halo-sharded mode)
+    bool full_act = false;         // xh/xl/x8lo/x8hi hold a whole L x L image (false: halo-sharded, they live in the window)
     std::vector<void*> allocs;
 };
 
@@ -206,13 +203,13 @@ struct dmp2_engine {
     float stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     void* tc_state = nullptr;        // tensor-core conv state (tensor maps), owned by conv_tc.cu
     void* vt_state = nullptr;        // tensor-core vgru state, owned by vgru_tc.cu
-    void* vp_state = nullptr;        // persistent tensor-core vgru state, owned by vgru_persist.cu
     int conv_cluster = 2;            // CTAs per cluster sharing the conv weight stream by TMA multicast (1 = off)
-    int vgru_mode = 0;               // 0 = tensor cores, one launch per MSA row; 1 = CUDA-core fp32 validation path; 2 = tensor cores, persistent kernel
+    int conv_sms = 0;                // SMs the persistent conv kernel occupies (0 = all)
+    int vgru_mode = 0;               // 0 = tensor cores, one launch per MSA row; 1 = CUDA-core fp32 validation path
     bool eig_no_cl16 = false;        // set when a 16-CTA cluster launch was refused
     bool attr_eig = false, attr_refine = false, attr_eig_grid = false;   // per-engine (= per-device) cudaFuncSetAttribute done
     StripCtx sp;                     // halo-sharded mode: window + peers (strip.cu)
-    bool fuse_stats = false;         // DMP2_FUSE_STATS=1: InstanceNorm sums in the conv epilogue instead of k_in_stats (tested, not faster)
+    bool fuse_stats = true;          // InstanceNorm sums come out of the conv epilogue (DMP2_FUSE_STATS=0: separate k_in_stats pass)
     bool strip_on = false;           // true while dmp2_fold_strip runs: the 2-D track works on rows [sp.r0, sp.r1)
     bool profile = false;            // record a CUDA-event pair around every conv launch (bench.py roofline)
     std::vector<cudaEvent_t> prof_ev;
@@ -238,8 +235,7 @@ int run_vgru(dmp2_engine* e, const uint8_t* msa, int N, int L, float* out, cudaS
 int run_vgru_ffma(dmp2_engine* e, const uint8_t* msa, int N, int L, float* out, cudaStream_t st);
 int run_vgru_tc(dmp2_engine* e, const uint8_t* msa, int N, int L, float* out, cudaStream_t st, int ld = 0);   // ld: row stride of msa (0 = L)
 void vgru_tc_destroy(dmp2_engine* e);
-int run_vgru_persist(dmp2_engine* e, const uint8_t* msa, int N, int L, float* out, cudaStream_t st);
-void vgru_persist_destroy(dmp2_engine* e);
+void vgru_tc_invalidate(dmp2_engine* e);
 int run_bigru(dmp2_engine* e, const BiGruLayer* layers, int nlayers, const float* in, int L, float* out, cudaStream_t st);
 int run_coord_head(dmp2_engine* e, const float* mat1d_t, const float* mds, int L, float* ca, cudaStream_t st);
 // resnet.cu
@@ -255,7 +251,8 @@ int run_head_post(dmp2_engine* e, const float* head2, int L, float* conf, float*
 int run_conv_tc(dmp2_engine* e, int blk, const __half* xh, const __half* xl, const uint8_t* x8lo, const uint8_t* x8hi, int L,
                 int H, int y_off, int map_rows, float* raw, int mode, cudaStream_t st, bool fuse_stats = false);
 bool conv_tc_fuses_stats(const dmp2_engine* e);      // true: run_conv_tc(..., fuse_stats = true) leaves ws.norm_ss / sp.totals ready
-int run_gemm_tn_test(dmp2_engine* e, const float* a, const float* b, int M, int N, int K, int mode, float* c, cudaStream_t st);
+int run_gemm_tn_test(dmp2_engine* e, const float* a, const float* b, int M, int N, int K, int mode, int chunk_k, float* c, cudaStream_t st);
+void conv_tc_invalidate(dmp2_engine* e);             // forget cached activation tensor maps (their buffers are being freed)
 void conv_tc_destroy(dmp2_engine* e);
 // eig.cu
 int run_eig_top8(dmp2_engine* e, const float* m, int L, float* vals, float* mds_scaled, float* vecs_raw, cudaStream_t st);

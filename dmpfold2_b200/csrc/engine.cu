@@ -212,6 +212,8 @@ static int load_weights(dmp2_engine* e, HostSD& sd) {
 // workspace
 // ---------------------------------------------------------------------------------------------------
 static void free_workspace(dmp2_engine* e) {
+    conv_tc_invalidate(e);               // cached tensor maps point into the buffers released here
+    vgru_tc_invalidate(e);
     for (void* p : e->ws.allocs) cudaFree(p);
     e->ws = Workspace();
 }
@@ -232,12 +234,15 @@ int ensure_workspace(dmp2_engine* e, int L, int N, int rows2d) {
     Workspace& ws = e->ws;
     if (rows2d < 0) rows2d = L;
     // halo-sharded folds keep only their strip of the 2-D track (and the conv operand copies in the window)
-    if (ws.L >= L && ws.N >= N && ((int64_t)ws.rows2d * ws.L >= (int64_t)rows2d * L)) return 0;
-    if (rows2d == L) { L = std::max(L, ws.L); rows2d = L; }
+    // (a halo-sharded workspace has no full-size conv operand copies -- they live in the IPC window -- so a whole-image
+    //  call must never reuse it, whatever the sizes say)
+    const bool want_full = rows2d == L;
+    if (ws.L >= L && ws.N >= N && ((int64_t)ws.rows2d * ws.L >= (int64_t)rows2d * L) && (!want_full || ws.full_act)) return 0;
+    if (want_full) { L = std::max(L, ws.L); rows2d = L; }
     N = std::max(N, ws.N);
     CUDA_TRY(e, cudaDeviceSynchronize());
     free_workspace(e);
-    const int64_t P = (int64_t)L * L, P2 = (int64_t)rows2d * L, PA = rows2d == L ? P : 1, Npad = (N + 3) & ~3, n = 21 * (int64_t)L, npad = (n + 63) & ~(int64_t)63;
+    const int64_t P = (int64_t)L * L, P2 = (int64_t)rows2d * L, PA = want_full ? P : 1, Npad = (N + 3) & ~3, n = 21 * (int64_t)L, npad = (n + 63) & ~(int64_t)63;
     TRY(wsalloc(e, &ws.msa, (int64_t)N * L));
     TRY(wsalloc(e, &ws.msa_t, (int64_t)L * Npad));
     TRY(wsalloc(e, &ws.seqw, N));
@@ -246,11 +251,11 @@ int ensure_workspace(dmp2_engine* e, int L, int N, int rows2d) {
     TRY(wsalloc(e, &ws.cov, npad * npad));
     TRY(wsalloc(e, &ws.gj_p, 4096));
     const int64_t Npad64 = (N + 63) & ~(int64_t)63, n4 = (n + 3) & ~(int64_t)3;
-    if (Npad64 < npad) {
-        TRY(wsalloc(e, &ws.xct, Npad * n4));
-        TRY(wsalloc(e, &ws.kmat, Npad64 * Npad64));
-        TRY(wsalloc(e, &ws.wy, Npad * n4));
-    }
+    // Woodbury buffers: always present.  The workspace is reused for every later (L', N') <= (L, N), and whether the
+    // Woodbury or the direct path runs depends on THAT call's N' vs 21 L', not on the sizes seen here.
+    TRY(wsalloc(e, &ws.xct, Npad * n4));
+    TRY(wsalloc(e, &ws.kmat, Npad64 * Npad64));
+    TRY(wsalloc(e, &ws.wy, Npad * n4));
     TRY(wsalloc(e, &ws.gj_r, 64 * std::max(npad, Npad64)));
     TRY(wsalloc(e, &ws.x3, P));
     TRY(wsalloc(e, &ws.apc, 2 * L + 1));
@@ -258,10 +263,6 @@ int ensure_workspace(dmp2_engine* e, int L, int N, int rows2d) {
     TRY(wsalloc(e, &ws.vg_h, 4 * (int64_t)L * 512));
     TRY(wsalloc(e, &ws.vt_h16, 8 * (int64_t)L * 512));
     TRY(wsalloc(e, &ws.vt_gi1, 2 * (int64_t)L * 1536));
-    TRY(wsalloc(e, &ws.vp_h16, 12 * (int64_t)L * 512));
-    TRY(wsalloc(e, &ws.vp_f32, 6 * (int64_t)L * 512));
-    TRY(wsalloc(e, &ws.vp_gi1, 4 * (int64_t)L * 1536));
-    TRY(wsalloc(e, &ws.vp_cnt, 3 * (int64_t)((L + 127) / 128)));
     TRY(wsalloc(e, &ws.v_last, (int64_t)L * 512));
     TRY(wsalloc(e, &ws.gi, (int64_t)L * 1536));
     TRY(wsalloc(e, &ws.seq_a, (int64_t)L * 520));
@@ -299,6 +300,7 @@ int ensure_workspace(dmp2_engine* e, int L, int N, int rows2d) {
     ws.L = L;
     ws.N = N;
     ws.rows2d = rows2d;
+    ws.full_act = want_full;
     return 0;
 }
 
@@ -424,13 +426,13 @@ int dmp2_create(dmp2_engine** out, int device, int n_tensors, const char* const*
         else if (!strcmp(mode, "f16f8")) e->conv_mode = DMP2_CONV_TC_F16F8;
     }
     const char* cc = getenv("DMP2_CONV_CLUSTER");
-    if (cc && (!strcmp(cc, "1") || !strcmp(cc, "2") || !strcmp(cc, "4"))) e->conv_cluster = atoi(cc);
-    if (cc && !strcmp(cc, "pair")) e->conv_cluster = 0;        // cta_group::2 CTA-pair kernel
+    if (cc && (!strcmp(cc, "1") || !strcmp(cc, "2"))) e->conv_cluster = atoi(cc);
+    const char* cs = getenv("DMP2_CONV_SMS");
+    if (cs && atoi(cs) > 0) e->conv_sms = atoi(cs);
     const char* vm = getenv("DMP2_VGRU");
     const char* fs = getenv("DMP2_FUSE_STATS");
     if (fs) e->fuse_stats = strcmp(fs, "0") != 0;
     if (vm && !strcmp(vm, "ffma")) e->vgru_mode = 1;
-    if (vm && !strcmp(vm, "persist")) e->vgru_mode = 2;
     if (vm && !strcmp(vm, "steps")) e->vgru_mode = 0;
     *out = e;
     return 0;
@@ -442,7 +444,6 @@ void dmp2_destroy(dmp2_engine* e) {
     cudaDeviceSynchronize();
     conv_tc_destroy(e);
     vgru_tc_destroy(e);
-    vgru_persist_destroy(e);
     strip_detach(e);
     free_workspace(e);
     for (void* p : e->weight_allocs) cudaFree(p);
@@ -687,11 +688,17 @@ int dmp2_backbone(dmp2_engine* e, const float* ca_dev, int L, float* out_dev, vo
     return run_backbone(e, ca_dev, nullptr, L, out_dev, nullptr, st);
 }
 
-int dmp2_gemm_tn_test(dmp2_engine* e, const float* a_dev, const float* b_dev, int M, int N, int K, int mode, float* c_dev,
-                      void* stream) {
+int dmp2_gemm_tn_test(dmp2_engine* e, const float* a_dev, const float* b_dev, int M, int N, int K, int mode, int chunk_k,
+                      float* c_dev, void* stream) {
     if (!e) return DMP2_ERR_BAD_ARG;
     TRY(check_device(e));
-    return run_gemm_tn_test(e, a_dev, b_dev, M, N, K, mode, c_dev, (cudaStream_t)stream);
+    return run_gemm_tn_test(e, a_dev, b_dev, M, N, K, mode, chunk_k, c_dev, (cudaStream_t)stream);
+}
+
+int dmp2_set_conv_sms(dmp2_engine* e, int sms) {
+    if (!e || sms < 0) return DMP2_ERR_BAD_ARG;
+    e->conv_sms = sms;
+    return 0;
 }
 
 }  // extern "C"

@@ -54,7 +54,6 @@ struct LoadConcat2 {             // A(m,k) = k < k1 ? p1[m*ld1+k] : p2[m*ld2 + k
 };
 
 int run_vgru(dmp2_engine* e, const uint8_t* msa, int N, int L, float* out, cudaStream_t st) {
-    if (e->vgru_mode == 2) return run_vgru_persist(e, msa, N, L, out, st);
     return e->vgru_mode == 0 ? run_vgru_tc(e, msa, N, L, out, st) : run_vgru_ffma(e, msa, N, L, out, st);
 }
 

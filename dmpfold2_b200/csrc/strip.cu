@@ -202,6 +202,7 @@ int strip_detach(dmp2_engine* e) {
     if (!sp.win) return 0;
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
+    conv_tc_invalidate(e);               // the conv's cached tensor maps point into the window
     if (sp.attached && sp.ipc)
         for (int r = 0; r < sp.world; r++)
             if (r != sp.rank && sp.peer[r]) cudaIpcCloseMemHandle(sp.peer[r]);

@@ -296,6 +296,10 @@ int run_vgru_tc(dmp2_engine* e, const uint8_t* msa, int N, int L, float* out, cu
     return 0;
 }
 
+void vgru_tc_invalidate(dmp2_engine* e) {             // the state buffers the cached tensor maps describe are being freed
+    if (e->vt_state) { ((VtState*)e->vt_state)->a_ptr = nullptr; ((VtState*)e->vt_state)->a_L = 0; }
+}
+
 void vgru_tc_destroy(dmp2_engine* e) {
     if (e->vt_state) {
         delete (VtState*)e->vt_state;

@@ -53,7 +53,8 @@ _SIGS = {
     'dmp2_coord_gru': (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
     'dmp2_refine': (_i, [_vp, _vp, _i, _i, _vp]),
     'dmp2_backbone': (_i, [_vp, _vp, _i, _vp, _vp]),
-    'dmp2_gemm_tn_test': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    'dmp2_gemm_tn_test': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    'dmp2_set_conv_sms': (_i, [_vp, _i]),
 }
 EXPORTS = tuple(_SIGS)
 
@@ -341,12 +342,16 @@ class Engine:
         self._check(self.lib.dmp2_backbone(self.h, _ptr(c), c.shape[0], _ptr(out), self._stream()), 'dmp2_backbone')
         return out
 
-    def gemm_tn_test(self, a, b, mode='f16x3') -> torch.Tensor:
+    def gemm_tn_test(self, a, b, mode='f16x3', chunk_k: int = 0) -> torch.Tensor:
+        """C = A B^T on the tensor-core GEMM core; chunk_k = length of one tcgen05 accumulation chain (0 = all of K)."""
         a = self._dev(a, torch.float32)
         b = self._dev(b, torch.float32)
         m, k = a.shape
         n = b.shape[0]
         out = self._empty(m, n)
-        self._check(self.lib.dmp2_gemm_tn_test(self.h, _ptr(a), _ptr(b), m, n, k, CONV_MODES[mode], _ptr(out), self._stream()),
-                    'dmp2_gemm_tn_test')
+        self._check(self.lib.dmp2_gemm_tn_test(self.h, _ptr(a), _ptr(b), m, n, k, CONV_MODES[mode], int(chunk_k), _ptr(out),
+                                               self._stream()), 'dmp2_gemm_tn_test')
         return out
+
+    def set_conv_sms(self, sms: int):
+        self._check(self.lib.dmp2_set_conv_sms(self.h, int(sms)), 'dmp2_set_conv_sms')

@@ -44,11 +44,12 @@ typedef enum {
 
 /* Convolution arithmetic of the sixteen 5x5 ResNet blocks (network.py:26 inside ResNet_Block). */
 typedef enum {
-    DMP2_CONV_TC_F16X3 = 0, /* tcgen05, fp16 hi+lo split of both operands, 3 MMAs, fp32 accumulate (parity mode) */
-    DMP2_CONV_TC_F16 = 1,   /* tcgen05, single fp16 MMA, fp32 accumulate (fast mode; ~1e-3 A drift)              */
+    DMP2_CONV_TC_F16X3 = 0, /* tcgen05, fp16 hi+lo split of both operands, 3 MMAs per MAC, per-tap accumulation chains
+                               summed in fp32 registers: as accurate as an fp32 CPU conv (parity mode)           */
+    DMP2_CONV_TC_F16 = 1,   /* tcgen05, single fp16 MMA (informational; ~1e-4 relative operand error)            */
     DMP2_CONV_FFMA = 2,     /* CUDA-core fp32 implicit GEMM (validation path for the tensor-core kernels)        */
     DMP2_CONV_TC_F16F8 = 3  /* tcgen05, fp16 main term + the two hi/lo correction terms in FP8 (e4m3 x e5m2): 2 MMA-
-                               equivalents per MAC, error ~2^-14 relative; the default                            */
+                               equivalents per MAC, operand error ~6e-6 relative (fast mode)                     */
 } dmp2_conv_mode;
 
 /* ---- lifetime ------------------------------------------------------------------------------------ */
@@ -153,9 +154,15 @@ int dmp2_refine(dmp2_engine* e, float* ca_dev, int L, int steps, void* stream);
 int dmp2_backbone(dmp2_engine* e, const float* ca_dev, int L, float* out_dev, void* stream);
 
 /* Generic fp32 GEMM self-test hook for the tensor-core GEMM core: C[M,N] = A[M,K] * B[N,K]^T through the
- * same tcgen05 pipeline the conv uses (mode as dmp2_conv_mode).  K % 64 == 0. */
-int dmp2_gemm_tn_test(dmp2_engine* e, const float* a_dev, const float* b_dev, int M, int N, int K, int mode,
+ * same tcgen05 pipeline the conv uses (mode as dmp2_conv_mode: f16 or f16x3).  K % 64 == 0, N % 4 == 0.
+ * chunk_k = length of one tcgen05 accumulation chain (a multiple of 64 dividing K; 0 = the whole K): the chains are
+ * summed in fp32 registers with round-to-nearest, exactly as the conv does per tap. */
+int dmp2_gemm_tn_test(dmp2_engine* e, const float* a_dev, const float* b_dev, int M, int N, int K, int mode, int chunk_k,
                       float* c_dev, void* stream);
+
+/* Tuning: number of SMs the persistent conv kernel occupies (0 = all).  A throughput scheduler that folds several
+ * targets on several streams leaves a few SMs to the latency-bound kernels of the other targets. */
+int dmp2_set_conv_sms(dmp2_engine* e, int sms);
 
 #ifdef __cplusplus
 }

@@ -71,9 +71,9 @@ def read_template_ca(path: str) -> np.ndarray:
 # ----------------------------------------------------------------------------------------------------
 # MSA features (predict.py:32-61)
 # ----------------------------------------------------------------------------------------------------
-def one_hot_msa(msa: torch.Tensor) -> torch.Tensor:
+def one_hot_msa(msa: torch.Tensor, dtype: torch.dtype = torch.float32) -> torch.Tensor:
     """predict.py:136 -- one_hot(clamp(codes, max=20), 21): gap (21) and unknown (20) share class 20."""
-    return F.one_hot(torch.clamp(msa.long(), max=20), 21).float()
+    return F.one_hot(torch.clamp(msa.long(), max=20), 21).to(dtype)
 
 
 def reweight(msa1hot: torch.Tensor, cutoff: float = 0.8) -> torch.Tensor:
@@ -82,7 +82,7 @@ def reweight(msa1hot: torch.Tensor, cutoff: float = 0.8) -> torch.Tensor:
     n, l, a = msa1hot.shape
     x = msa1hot.reshape(n, l * a)
     id_mtx = x @ x.t()
-    return 1.0 / (id_mtx > id_min).float().sum(dim=-1)
+    return 1.0 / (id_mtx > id_min).to(msa1hot.dtype).sum(dim=-1)
 
 
 def fast_dca(msa1hot: torch.Tensor, weights: torch.Tensor, penalty: float = 4.5) -> torch.Tensor:
@@ -93,25 +93,26 @@ def fast_dca(msa1hot: torch.Tensor, weights: torch.Tensor, penalty: float = 4.5)
     mean = (x * weights[:, None]).sum(dim=0, keepdim=True) / num_points
     x = (x - mean) * torch.sqrt(weights[:, None])
     cov = (x.t() @ x) / num_points
-    cov_reg = cov + torch.eye(nc * ns, device=x.device) * penalty / torch.sqrt(weights.sum())
+    cov_reg = cov + torch.eye(nc * ns, device=x.device, dtype=x.dtype) * penalty / torch.sqrt(weights.sum())
     inv_cov = torch.linalg.inv(cov_reg)
     x1 = inv_cov.view(nc, ns, nc, ns)
     features = x1.transpose(1, 2).contiguous().reshape(nc, nc, ns * ns)
-    eye = torch.eye(nc, device=x.device)
+    eye = torch.eye(nc, device=x.device, dtype=x.dtype)
     x3 = torch.sqrt((x1[:, :-1, :, :-1] ** 2).sum(dim=(1, 3))) * (1 - eye)
     apc = x3.sum(dim=0, keepdim=True) * x3.sum(dim=1, keepdim=True) / x3.sum()
     contacts = (x3 - apc) * (1 - eye)
     return torch.cat((features, contacts[:, :, None]), dim=2)
 
 
-def msa_features(msa: torch.Tensor) -> torch.Tensor:
-    """predict.py:136-140 -- (L,L,442) DCA features, zeros for a single sequence."""
+def msa_features(msa: torch.Tensor, dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """predict.py:136-140 -- (L,L,442) DCA features, zeros for a single sequence.
+    dtype=float64 is the ground-truth arm of the precision triangulation (tools/fp64_triangulate.py)."""
     nseqs, length = msa.shape
-    hot = one_hot_msa(msa)
+    hot = one_hot_msa(msa, dtype)
     w = reweight(hot, 0.8)
     if nseqs > 1:
-        return fast_dca(hot, w).float()
-    return torch.zeros((length, length, 442), device=msa.device)
+        return fast_dca(hot, w).to(dtype)
+    return torch.zeros((length, length, 442), device=msa.device, dtype=dtype)
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -227,7 +228,7 @@ def head_to_mds(x2: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Ten
     conf = x2[:, 1].mean(dim=2)
     dm = torch.abs((dm + dm.transpose(1, 2)) / 2)
     m = 0.5 * (dm[:, 0:1, :].expand(-1, nres, -1) ** 2 + dm[:, :, 0:1].expand(-1, -1, nres) ** 2 - dm ** 2)
-    w, v = symeig_canonical(m.float())
+    w, v = symeig_canonical(m if m.dtype == torch.float64 else m.float())
     w = torch.clamp(F.relu(w), min=1e-8)
     mds = torch.matmul(v, torch.diag_embed(w.sqrt()))[:, :, -8:]
     return conf, m, mds
@@ -241,7 +242,7 @@ def refine_coords(coords: torch.Tensor, n_steps: int) -> torch.Tensor:
     for _ in range(n_steps):
         diffs = coords.unsqueeze(0) - coords.unsqueeze(1)          # [i,j] = c_j - c_i
         dists = diffs.norm(dim=2).clamp(min=0.01, max=10.0)
-        viol = (dists < 3.0).float() * (3.0 - dists)
+        viol = (dists < 3.0).to(coords.dtype) * (3.0 - dists)
         accels = ((100.0 * viol).unsqueeze(2) * (diffs / dists.unsqueeze(2))).sum(dim=0)
         d = coords[1:] - coords[:-1]
         dd = d.norm(dim=1).clamp(min=0.1)
@@ -292,25 +293,29 @@ def calpha_to_main_chain(ca: torch.Tensor) -> torch.Tensor:
 class Oracle:
     """Holds the weights (a state_dict as loaded by predict.py:89-92) and runs the reference algorithm."""
 
-    def __init__(self, state_dict: Dict[str, torch.Tensor], device: str = 'cpu'):
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device: str = 'cpu', dtype: torch.dtype = torch.float32):
         # device='cpu' is the oracle proper.  A cuda device only serves tools/torch_cuda_bar.py, which times the same
         # algorithm on PyTorch's library kernels (cuDNN/cuBLAS/cuSOLVER) as the "existing Blackwell kernels" bar.
+        # dtype=float32 is the reference's arithmetic (the parity target); dtype=float64 runs the SAME algorithm with
+        # the same (fp32-valued) weights in double precision -- the ground truth both the reference and the engine are
+        # measured against in tools/fp64_triangulate.py.
         self.device = torch.device(device)
-        self.sd = {k: v.detach().float().to(self.device) for k, v in state_dict.items()}
-        self._vgru = _nn_gru(self.sd, 'vgru', 22, 512, 2, False).to(self.device)
-        self._hgru = _nn_gru(self.sd, 'hgru', 512, 256, 2, True).to(self.device)
-        self._cgru = _nn_gru(self.sd, 'coord_gru', 520, 256, 3, True).to(self.device)
+        self.dtype = dtype
+        self.sd = {k: v.detach().float().to(dtype).to(self.device) for k, v in state_dict.items()}
+        self._vgru = _nn_gru(self.sd, 'vgru', 22, 512, 2, False).to(self.device).to(dtype)
+        self._hgru = _nn_gru(self.sd, 'hgru', 512, 256, 2, True).to(self.device).to(dtype)
+        self._cgru = _nn_gru(self.sd, 'coord_gru', 520, 256, 3, True).to(self.device).to(dtype)
 
     # -- 1-D track: network.py:223-226
     def mat1d(self, msa: torch.Tensor) -> torch.Tensor:
         """(N,L) codes -> (512,L).  embed is the identity (network.py:188) so the input is one_hot(.,22)."""
-        x = F.one_hot(msa.long(), 22).float()
+        x = F.one_hot(msa.long(), 22).to(self.dtype)
         v = self._vgru(x)[0][-1]                                  # (L,512): state after the last MSA row
         h = self._hgru(v.unsqueeze(1))[0]                         # (L,1,512)
         return h.permute(1, 2, 0)[0]                              # (512,L)
 
     def vgru_last(self, msa: torch.Tensor) -> torch.Tensor:
-        return self._vgru(F.one_hot(msa.long(), 22).float())[0][-1]
+        return self._vgru(F.one_hot(msa.long(), 22).to(self.dtype))[0][-1]
 
     def hgru_out(self, v: torch.Tensor) -> torch.Tensor:
         return self._hgru(v.unsqueeze(1))[0][:, 0]
@@ -362,12 +367,12 @@ class Oracle:
         msa_t = torch.from_numpy(np.ascontiguousarray(msa)).long().to(self.device)
         length = msa_t.shape[1]
         with torch.no_grad():
-            feats = msa_features(msa_t).permute(2, 0, 1).unsqueeze(0)
+            feats = msa_features(msa_t, self.dtype).permute(2, 0, 1).unsqueeze(0)
             if template_ca is not None:
-                c = torch.from_numpy(template_ca).float().unsqueeze(0).to(self.device)
+                c = torch.from_numpy(template_ca).float().to(self.dtype).unsqueeze(0).to(self.device)
                 dmap = (c - c.transpose(0, 1)).pow(2).sum(dim=2).sqrt()[None, None]
             else:
-                dmap = torch.zeros((1, 1, length, length), device=self.device) - 1
+                dmap = torch.zeros((1, 1, length, length), device=self.device, dtype=self.dtype) - 1
             x2 = torch.cat((feats, dmap), dim=1)
             if taps is not None:
                 taps['x2'] = x2

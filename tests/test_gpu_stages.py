@@ -200,15 +200,37 @@ def test_bad_arguments_return_errors(eng):
 
 
 @pytest.mark.parametrize('mode,tol', [('f16x3', 5e-5), ('f16', 2e-3)])
-@pytest.mark.parametrize('m,k', [(128, 64), (300, 256), (1000, 3200)])
-def test_tensor_core_gemm_core(eng, mode, tol, m, k):
-    """TMA -> tcgen05 -> TMEM pipeline self-test on a plain GEMM (descriptors, swizzle, barriers, epilogue)."""
+@pytest.mark.parametrize('m,n,k,chunk', [(128, 512, 64, 0), (300, 512, 256, 128), (1000, 512, 3200, 128), (777, 384, 1024, 256),
+                                         (200, 36, 128, 64)])
+def test_tensor_core_gemm_core(eng, mode, tol, m, n, k, chunk):
+    """TMA -> tcgen05 -> TMEM pipeline self-test on a plain GEMM (descriptors, swizzle, barriers, the double-buffered
+    chunk accumulators and the register running sums), ragged M and N included."""
     g = torch.Generator().manual_seed(m + k)
     a = torch.randn(m, k, generator=g)
-    b = torch.randn(512, k, generator=g) * 0.1
+    b = torch.randn(n, k, generator=g) * 0.1
     ref = a.double() @ b.double().t()
-    got = eng.gemm_tn_test(a, b, mode).cpu().double()
+    got = eng.gemm_tn_test(a, b, mode, chunk).cpu().double()
     assert _rel(got, ref) < tol, _rel(got, ref)
+
+
+def test_two_level_accumulation_matches_fp32_cpu_gemm(eng):
+    """The point of the per-tap accumulation chains: with chains of K=128 summed in fp32 registers the tensor-core
+    GEMM is as close to the exact product as torch's fp32 CPU GEMM (within 2x), while ONE chain over K=3200 is an order
+    of magnitude further away (tcgen05 accumulators truncate on every MMA)."""
+    g = torch.Generator().manual_seed(5)
+    a = torch.randn(640, 3200, generator=g)
+    b = torch.randn(512, 3200, generator=g)
+    exact = a.double() @ b.double().t()
+
+    def resid(y):                                # error after removing a uniform scale (InstanceNorm absorbs that part)
+        e = y.double() - exact
+        e = e - float((e * exact).sum() / (exact * exact).sum()) * exact
+        return float(e.pow(2).mean().sqrt() / exact.pow(2).mean().sqrt())
+    cpu = resid(a @ b.t())
+    chained = resid(eng.gemm_tn_test(a, b, 'f16x3', 128).cpu())
+    single = resid(eng.gemm_tn_test(a, b, 'f16x3', 0).cpu())
+    print(f'fp32 CPU GEMM {cpu:.2e}, tcgen05 chains of 128: {chained:.2e}, one chain: {single:.2e}')
+    assert chained < 2 * cpu and single > 3 * chained
 
 
 def test_vgru_long_wavefront(eng, oracle, pf10963):
@@ -221,12 +243,14 @@ def test_vgru_long_wavefront(eng, oracle, pf10963):
     assert (one - oracle.vgru_last(torch.from_numpy(msa[:1]))).abs().max() < 1e-5
 
 
-@pytest.mark.parametrize('cluster', ['pair', '1', '4'])
-def test_conv_cluster_variants(state_dict, oracle, cluster, monkeypatch):
-    """The conv kernel variants that share the weight stream differently (cta_group::2 CTA pairs, no cluster,
-    4-CTA multicast) must agree with the oracle exactly like the default (2-CTA multicast)."""
+@pytest.mark.parametrize('cluster,sms', [('1', '0'), ('2', '20'), ('1', '3')])
+def test_conv_cluster_variants(state_dict, oracle, cluster, sms, monkeypatch):
+    """The persistent conv kernel without weight multicast (cluster of 1), and on a restricted number of SMs (every
+    CTA then walks through many work units: exercises the tile scheduler, both TMEM chunk buffers' phase wrap-around
+    and the cross-unit InstanceNorm sums), must agree with the oracle exactly like the default (2-CTA multicast)."""
     from dmpfold2_b200.engine import Engine
     monkeypatch.setenv('DMP2_CONV_CLUSTER', cluster)
+    monkeypatch.setenv('DMP2_CONV_SMS', sms)
     e = Engine(state_dict, 0)
     try:
         g = torch.Generator().manual_seed(77)
