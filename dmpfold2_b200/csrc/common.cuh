@@ -189,7 +189,7 @@ struct StripCtx {
 struct dmp2_engine {
     int device = 0;
     int num_sms = 148;
-    int conv_mode = DMP2_CONV_TC_F16F8;
+    int conv_mode = DMP2_CONV_TC_F16X3;   // parity mode; DMP2_CONV_MODE=f16f8 is the fast mode (operand error ~6e-6 relative)
     int64_t launches = 0;
     int status = 0;
     std::string err;
@@ -203,8 +203,9 @@ struct dmp2_engine {
     float stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     void* tc_state = nullptr;        // tensor-core conv state (tensor maps), owned by conv_tc.cu
     void* vt_state = nullptr;        // tensor-core vgru state, owned by vgru_tc.cu
-    int conv_cluster = 2;            // CTAs per cluster sharing the conv weight stream by TMA multicast (1 = off)
+    int conv_cluster = 0;            // conv kernel form: 0 = cta_group::2 CTA pairs, 1 = independent CTAs, 2 = 2-CTA weight multicast (DMP2_CONV_CLUSTER=pair|1|2)
     int conv_sms = 0;                // SMs the persistent conv kernel occupies (0 = all)
+    int conv_chunk_taps = 1;         // taps per tcgen05 accumulation chain (1, 5 or 25; DMP2_CONV_CHUNK): longer chains = fewer TMEM drains, larger truncation error
     int vgru_mode = 0;               // 0 = tensor cores, one launch per MSA row; 1 = CUDA-core fp32 validation path
     bool eig_no_cl16 = false;        // set when a 16-CTA cluster launch was refused
     bool attr_eig = false, attr_refine = false, attr_eig_grid = false;   // per-engine (= per-device) cudaFuncSetAttribute done

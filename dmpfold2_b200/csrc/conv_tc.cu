@@ -3,11 +3,17 @@
 //   M = L*L pixels, N = 512 output channels, K = 25 taps x 128 input channels.
 //
 // PERSISTENT kernel, one CTA per SM.  A work unit is a 128-pixel tile (8 rows x 16 columns) x 256 output channels.
+// Default form: CTA PAIRS (cta_group::2).  The two CTAs of a cluster own two pixel tiles and behave as one 256 x 256
+// tile: every MMA is M=256 N=256, issued by the leader CTA, reading the A rows of both CTAs and HALF of the B piece
+// from each CTA's shared memory.  What bounds this kernel once the epilogue is overlapped is the operand stream into
+// the SM (measured ceiling ~45-55 bytes/clock/SM whatever the precision mode, profiles/round2_conv_recut.txt); the
+// pair form needs 128 KB per SM per tap instead of 192 KB, which puts the fp16x3 mode under that ceiling.
+// (cta_group::1 forms with or without TMA multicast of the weights are kept as validation variants.)
 //
 //   warp 0       TMA producer: cp.async.bulk.tensor (128B swizzle; out-of-bounds zero fill = the pad-2 border) into an
 //                A ring (shifted pixel patch) and a B ring (256-cout weight pieces, multicast across a CTA cluster)
 //   warp 1       TMEM allocator + single-thread tcgen05.mma issuer, M=128 N=256
-//   warps 2..3   idle (they complete the first warpgroup, which gives its registers away: setmaxnreg 64)
+//   warps 2..3   idle (they complete the first warpgroup, which gives its registers away: setmaxnreg 56)
 //   warps 4..11  epilogue (two warpgroups, setmaxnreg 224): drain tensor memory into registers
 //
 // TWO-LEVEL ACCUMULATION.  The tcgen05 fp32 accumulator truncates (round-toward-zero) on every MMA: one chain over all
@@ -40,18 +46,19 @@ constexpr int A_BYTES = TILE_M * 128;     // 16 KB: 128 pixels x 128 bytes (64 f
 constexpr int B_BYTES = TILE_N * 128;     // 32 KB: one B piece = 256 couts x 128 bytes
 constexpr int BQ_ROWS = 64;               // TMA granule of a B piece (multicast unit)
 constexpr int BQ_BYTES = BQ_ROWS * 128;
-constexpr int NUM_B_SLOTS = 5;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int FIRST_EPI_WARP = 4;
 constexpr int NUM_THREADS = (FIRST_EPI_WARP + NUM_EPI_WARPS) * 32;
 enum { M_F16 = 0, M_F16X3 = 1, M_F16F8 = 2 };
 
-template <int MODE>
+template <int MODE, bool PAIR>
 struct Cfg {
     static constexpr int A_STAGE_BYTES = MODE == M_F16 ? A_BYTES : 2 * A_BYTES;
-    static constexpr int NUM_A_STAGES = MODE == M_F16 ? 4 : 2;
+    static constexpr int NUM_A_STAGES = PAIR ? (MODE == M_F16 ? 6 : 3) : (MODE == M_F16 ? 4 : 2);
     static constexpr int PIECES = MODE == M_F16 ? 1 : 2;      // B pieces per k-block
-    static constexpr int SMEM_BYTES = NUM_A_STAGES * A_STAGE_BYTES + NUM_B_SLOTS * B_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int B_SLOT_BYTES = PAIR ? B_BYTES / 2 : B_BYTES;     // a CTA of a pair holds 128 of the piece's 256 couts
+    static constexpr int NUM_B_SLOTS = PAIR ? 8 : 5;
+    static constexpr int SMEM_BYTES = NUM_A_STAGES * A_STAGE_BYTES + NUM_B_SLOTS * B_SLOT_BYTES + 1024 /*align*/ + 512 /*barriers*/;
 };
 
 struct ConvMaps {
@@ -114,6 +121,15 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
         : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// One lane of the (converged) warp.  The producer and issuer warps run their loops with ALL lanes (warp-uniform control
+// flow and operands) and only the TMA / MMA / commit instructions are guarded by this: the single-thread instructions then
+// take their operands from uniform registers instead of a per-instruction R2UR + ELECT + retry loop (which made the
+// issuer the bottleneck: ~21 SASS instructions per tcgen05.mma, profiles/round2_conv_recut.txt).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 
 // Sum v[i] over the 32 lanes of the warp; lane l ends up with the total of v[l] in v[0] (31 shuffles).
 __device__ __forceinline__ float lane_transpose_sum(float (&v)[32], int lane) {
@@ -151,14 +167,18 @@ __device__ __forceinline__ Unit decode_unit(const TcParams& p, int cu, uint32_t 
 // ---- the kernel --------------------------------------------------------------------------------------
 // CL = CTAs per cluster sharing the weight (B) stream: each CTA loads 1/CL of every B piece and multicasts it to all
 // CTAs of the cluster, which work on CL different pixel tiles of the SAME 256 output channels in lock step.
-template <int MODE, int CL>
+// PAIR: the cluster is one cta_group::2 CTA pair (see the header comment); CL must be 2.
+template <int MODE, int CL, bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv5_tc(const __grid_constant__ ConvMaps maps, const TcParams p) {
-    using C = Cfg<MODE>;
+    using C = Cfg<MODE, PAIR>;
+    constexpr int NUM_B_SLOTS = C::NUM_B_SLOTS;
+    constexpr int B_SLOT = C::B_SLOT_BYTES;
+    static_assert(!PAIR || CL == 2, "a CTA pair is a cluster of two");
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // 128B swizzle needs 1024-byte alignment
     const uint32_t a_base = base;
     const uint32_t b_base = base + C::NUM_A_STAGES * C::A_STAGE_BYTES;
-    const uint32_t bar_base = b_base + NUM_B_SLOTS * B_BYTES;
+    const uint32_t bar_base = b_base + NUM_B_SLOTS * B_SLOT;
     auto a_full = [&](int s) { return bar_base + 8u * s; };
     auto a_empty = [&](int s) { return bar_base + 8u * (C::NUM_A_STAGES + s); };
     auto b_full = [&](int s) { return bar_base + 8u * (2 * C::NUM_A_STAGES + s); };
@@ -171,18 +191,27 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv5_tc(const __grid_consta
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t crank = CL > 1 ? cluster_ctarank() : 0;
+    const bool leader = crank == 0;
     constexpr uint16_t MC_MASK = (uint16_t)((1u << CL) - 1);
     const int cluster_id = blockIdx.x / CL, num_clusters = gridDim.x / CL;
     const int chunks_per_unit = p.num_kb / p.chunk_kb;
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < C::NUM_A_STAGES; s++) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
-        for (int s = 0; s < NUM_B_SLOTS; s++) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), CL); }
-        for (int s = 0; s < 2; s++) { mbar_init(c_full(s), 1); mbar_init(c_empty(s), NUM_EPI_WARPS); }
+        for (int s = 0; s < NUM_B_SLOTS; s++) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), PAIR ? 1 : CL); }
+        // pair: the leader's issuer waits for the epilogue warps of BOTH CTAs before it reuses a chunk accumulator
+        for (int s = 0; s < 2; s++) { mbar_init(c_full(s), 1); mbar_init(c_empty(s), PAIR ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (warp == 1) {
+    if (PAIR) {
+        __syncthreads();
+        cluster_sync_all();
+        if (warp == 1) {                             // both CTAs, same logical warp, same destination offset
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        }
+    } else if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -191,12 +220,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv5_tc(const __grid_consta
     if (CL > 1) cluster_sync_all();                  // peers' barriers must be initialised before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
-    // register re-distribution between the warpgroups (the epilogue holds 128 running sums per thread)
+    // register re-distribution between the warpgroups (the epilogue holds 128 running sums per thread).  The CTA is
+    // launched with 168 registers x 384 threads = 64512; 128 x 56 + 256 x 224 uses exactly that pool (asking for more
+    // would block setmaxnreg.inc forever).
     if (warp < FIRST_EPI_WARP) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
+        // ===================== TMA producer (whole warp, one elected lane issues) =====================
+        {
             int sa = 0, pa = 0, sb = 0, pb = 0;
             for (int cu = cluster_id; cu < p.units; cu += num_clusters) {
                 const Unit u = decode_unit<CL>(p, cu, crank);
@@ -210,21 +241,31 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv5_tc(const __grid_consta
                         c1 = u.x0 + dx - 2; c2 = u.y0 + dy - 2 + p.y_off;
                     }
                     mbar_wait(a_empty(sa), pa ^ 1);
-                    mbar_expect_tx(a_full(sa), C::A_STAGE_BYTES);
+                    // pair: the loads of both CTAs signal the LEADER's barrier, which expects the bytes of both
+                    const uint32_t afl = PAIR ? mapa_u32(a_full(sa), 0) : a_full(sa);
                     const uint32_t ast = a_base + sa * C::A_STAGE_BYTES;
+                    if (elect_one()) {
+                    if (!PAIR) mbar_expect_tx(a_full(sa), C::A_STAGE_BYTES);
+                    else if (leader) mbar_expect_tx(a_full(sa), 2 * C::A_STAGE_BYTES);
+                    auto load_a = [&](uint32_t dst, const CUtensorMap* m, int c0) {
+                        if (PAIR) tma2_load_3d(dst, m, afl, c0, c1, c2);
+                        else tma_load_3d(dst, m, afl, c0, c1, c2);
+                    };
                     if (MODE == M_F16) {
-                        tma_load_3d(ast, &maps.a_hi, a_full(sa), p.gemm ? kb * KCHUNK : sub * KCHUNK, c1, c2);
+                        load_a(ast, &maps.a_hi, p.gemm ? kb * KCHUNK : sub * KCHUNK);
                     } else if (MODE == M_F16X3) {
                         const int c0 = p.gemm ? kb * KCHUNK : sub * KCHUNK;
-                        tma_load_3d(ast, &maps.a_hi, a_full(sa), c0, c1, c2);
-                        tma_load_3d(ast + A_BYTES, &maps.a_lo, a_full(sa), c0, c1, c2);
+                        load_a(ast, &maps.a_hi, c0);
+                        load_a(ast + A_BYTES, &maps.a_lo, c0);
                     } else if (sub == 0) {                         // F16F8: the two fp8 correction operands (128 channels each)
-                        tma_load_3d(ast, &maps.a8_lo, a_full(sa), 0, c1, c2);
-                        tma_load_3d(ast + A_BYTES, &maps.a8_hi, a_full(sa), 0, c1, c2);
+                        load_a(ast, &maps.a8_lo, 0);
+                        load_a(ast + A_BYTES, &maps.a8_hi, 0);
                     } else {                                       // F16F8: both fp16 channel chunks of x_hi
-                        tma_load_3d(ast, &maps.a_hi, a_full(sa), 0, c1, c2);
-                        tma_load_3d(ast + A_BYTES, &maps.a_hi, a_full(sa), KCHUNK, c1, c2);
+                        load_a(ast, &maps.a_hi, 0);
+                        load_a(ast + A_BYTES, &maps.a_hi, KCHUNK);
                     }
+                    }
+                    __syncwarp();
                     if (++sa == C::NUM_A_STAGES) { sa = 0; pa ^= 1; }
                     // ---- B pieces
                     for (int piece = 0; piece < C::PIECES; piece++) {
@@ -238,24 +279,55 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv5_tc(const __grid_consta
                             k0 = kb * KCHUNK;                      // weights are [512][K] with k = tap*128 + c = kb*64 + ...
                         }
                         mbar_wait(b_empty(sb), pb ^ 1);
-                        mbar_expect_tx(b_full(sb), B_BYTES);
-                        const uint32_t bdst = b_base + sb * B_BYTES;
+                        const uint32_t bdst = b_base + sb * B_SLOT;
+                        if (elect_one()) {
+                        if (PAIR) {                                // my 128 couts of the piece, as two 64-row boxes
+                            const uint32_t bfl = mapa_u32(b_full(sb), 0);
+                            if (leader) mbar_expect_tx(b_full(sb), 2 * B_SLOT);
+                            const int nr = u.n0 + (int)crank * 128;
+                            tma2_load_2d(bdst, bm, bfl, k0, nr);
+                            tma2_load_2d(bdst + BQ_BYTES, bm, bfl, k0, nr + BQ_ROWS);
+                        } else {
+                            mbar_expect_tx(b_full(sb), B_BYTES);
 #pragma unroll
-                        for (int i = 0; i < 4 / CL; i++) {         // my quarters of the piece, delivered to every CTA of the cluster
-                            const int qd = crank * (4 / CL) + i;
-                            if (CL == 1) tma_load_2d(bdst + qd * BQ_BYTES, bm, b_full(sb), k0, u.n0 + qd * BQ_ROWS);
-                            else tma_load_2d_mc(bdst + qd * BQ_BYTES, bm, b_full(sb), k0, u.n0 + qd * BQ_ROWS, MC_MASK);
+                            for (int i = 0; i < 4 / CL; i++) {     // my quarters of the piece, delivered to every CTA of the cluster
+                                const int qd = crank * (4 / CL) + i;
+                                if (CL == 1) tma_load_2d(bdst + qd * BQ_BYTES, bm, b_full(sb), k0, u.n0 + qd * BQ_ROWS);
+                                else tma_load_2d_mc(bdst + qd * BQ_BYTES, bm, b_full(sb), k0, u.n0 + qd * BQ_ROWS, MC_MASK);
+                            }
                         }
+                        }
+                        __syncwarp();
                         if (++sb == NUM_B_SLOTS) { sb = 0; pb ^= 1; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc(TILE_M, TILE_N);
-            const uint32_t idesc8 = make_idesc_f8(TILE_M, TILE_N);
+        // ===================== MMA issuer (whole warp, one elected lane issues; pair: the leader CTA only) ==========
+        if (!PAIR || leader) {
+            const uint32_t idesc = make_idesc(PAIR ? 2 * TILE_M : TILE_M, TILE_N);
+            const uint32_t idesc8 = make_idesc_f8(PAIR ? 2 * TILE_M : TILE_M, TILE_N);
+            // 4 MMAs over one 128-byte swizzle row of K: the descriptors advance by 32 bytes (2 units of 16) per MMA
+            auto mma16x4 = [&](uint32_t d, uint64_t da, uint64_t db, bool first) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (PAIR) tc2_mma_f16(d, da + 2 * k, db + 2 * k, idesc, !(first && k == 0));
+                    else tc_mma_f16(d, da + 2 * k, db + 2 * k, idesc, !(first && k == 0));
+                }
+            };
+            auto mma8x4 = [&](uint32_t d, uint64_t da, uint64_t db, bool first) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (PAIR) tc2_mma_f8(d, da + 2 * k, db + 2 * k, idesc8, !(first && k == 0));
+                    else tc_mma_f8(d, da + 2 * k, db + 2 * k, idesc8, !(first && k == 0));
+                }
+            };
+            auto commit = [&](uint32_t bar, bool shared_slot) {            // shared_slot: a B slot every CTA of the cluster waits for
+                if (PAIR) tc2_commit_mc(bar, 3);
+                else if (shared_slot && CL > 1) tc_commit_mc(bar, MC_MASK);
+                else tc_commit(bar);
+            };
             int sa = 0, pa = 0, sb = 0, pb = 0;
             uint32_t cc = 0;                                      // chunk counter over the whole kernel: buffer cc & 1
             for (int cu = cluster_id; cu < p.units; cu += num_clusters) {
@@ -269,41 +341,34 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv5_tc(const __grid_consta
                     }
                     const uint32_t d = tmem_base + cs * (uint32_t)TILE_N;
                     mbar_wait(a_full(sa), pa);
-                    const uint32_t a0 = a_base + sa * C::A_STAGE_BYTES;
-                    const uint32_t a1 = a0 + A_BYTES;
+                    const uint64_t da0 = make_smem_desc(a_base + sa * C::A_STAGE_BYTES);
+                    const uint64_t da1 = make_smem_desc(a_base + sa * C::A_STAGE_BYTES + A_BYTES);
+#pragma unroll
                     for (int piece = 0; piece < C::PIECES; piece++) {
                         mbar_wait(b_full(sb), pb);
                         tc_fence_after();
-                        const uint32_t b_addr = b_base + sb * B_BYTES;
+                        const uint64_t db = make_smem_desc(b_base + sb * B_SLOT);
                         const bool first = in_chunk == 0 && piece == 0;               // first MMA of the chain overwrites
-                        if (MODE == M_F16F8) {
-                            const uint32_t a = piece ? a1 : a0;
-                            if (sub == 0) {
-#pragma unroll
-                                for (int k = 0; k < 4; k++)        // corrections first: K = 32 fp8 elements = 32 bytes per MMA
-                                    tc_mma_f8(d, make_smem_desc(a + k * 32), make_smem_desc(b_addr + k * 32), idesc8, !(first && k == 0));
+                        if (elect_one()) {
+                            if (MODE == M_F16F8) {
+                                if (sub == 0) mma8x4(d, piece ? da1 : da0, db, first);   // corrections first (K = 32 fp8 per MMA)
+                                else mma16x4(d, piece ? da1 : da0, db, first);
                             } else {
-#pragma unroll
-                                for (int k = 0; k < 4; k++)
-                                    tc_mma_f16(d, make_smem_desc(a + k * 32), make_smem_desc(b_addr + k * 32), idesc, !(first && k == 0));
+                                mma16x4(d, da0, db, first);                            // piece 0: hi(A) x hi(B); piece 1: hi(A) x lo(B)
+                                if (MODE == M_F16X3 && piece == 0) mma16x4(d, da1, db, false);   // lo(A) x hi(B)
                             }
-                        } else {
-#pragma unroll
-                            for (int k = 0; k < 4; k++)            // piece 0: hi(A) x hi(B); piece 1: hi(A) x lo(B)
-                                tc_mma_f16(d, make_smem_desc(a0 + k * 32), make_smem_desc(b_addr + k * 32), idesc, !(first && k == 0));
-                            if (MODE == M_F16X3 && piece == 0) {                      // lo(A) x hi(B)
-#pragma unroll
-                                for (int k = 0; k < 4; k++)
-                                    tc_mma_f16(d, make_smem_desc(a1 + k * 32), make_smem_desc(b_addr + k * 32), idesc, 1u);
-                            }
+                            commit(b_empty(sb), true);             // the slot is free only when every CTA of the cluster is done with it
                         }
-                        if (CL == 1) tc_commit(b_empty(sb));
-                        else tc_commit_mc(b_empty(sb), MC_MASK);   // the slot is free only when every CTA of the cluster is done with it
+                        __syncwarp();
                         if (++sb == NUM_B_SLOTS) { sb = 0; pb ^= 1; }
                     }
-                    tc_commit(a_empty(sa));
+                    if (elect_one()) {
+                        commit(a_empty(sa), false);
+                        if (in_chunk == p.chunk_kb - 1) commit(c_full(cs), false);    // chain finished: hand it to the epilogue
+                    }
+                    __syncwarp();
                     if (++sa == C::NUM_A_STAGES) { sa = 0; pa ^= 1; }
-                    if (in_chunk == p.chunk_kb - 1) { tc_commit(c_full(cs)); cc++; }   // chain finished: hand it to the epilogue
+                    if (in_chunk == p.chunk_kb - 1) cc++;
                 }
             }
         }
@@ -342,7 +407,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv5_tc(const __grid_consta
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(c_empty(cs));
+                if (lane == 0) {
+                    if (PAIR && !leader)
+                        asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(mapa_u32(c_empty(cs), 0)) : "memory");
+                    else mbar_arrive(c_empty(cs));
+                }
             }
             // ---- unit epilogue (the issuer is already filling the next unit's chunks)
             if (p.gemm) {
@@ -447,7 +516,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv5_tc(const __grid_consta
     if (CL > 1) cluster_sync_all();                  // no CTA may exit while a peer can still arrive on its barriers
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
     }
 }
 
@@ -461,9 +531,9 @@ struct TcState {
     bool attr_set = false;
 };
 
-template <int MODE, int CL>
+template <int MODE, int CL, bool PAIR>
 int set_attr(dmp2_engine* e) {
-    CUDA_TRY(e, cudaFuncSetAttribute(k_conv5_tc<MODE, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<MODE>::SMEM_BYTES));
+    CUDA_TRY(e, cudaFuncSetAttribute(k_conv5_tc<MODE, CL, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<MODE, PAIR>::SMEM_BYTES));
     return 0;
 }
 
@@ -474,9 +544,9 @@ int get_state(dmp2_engine* e, TcState** out) {
     }
     TcState* s = (TcState*)e->tc_state;
     if (!s->attr_set) {
-        TRY((set_attr<M_F16, 1>(e))); TRY((set_attr<M_F16, 2>(e)));
-        TRY((set_attr<M_F16X3, 1>(e))); TRY((set_attr<M_F16X3, 2>(e)));
-        TRY((set_attr<M_F16F8, 1>(e))); TRY((set_attr<M_F16F8, 2>(e)));
+        TRY((set_attr<M_F16, 1, false>(e))); TRY((set_attr<M_F16, 2, false>(e))); TRY((set_attr<M_F16, 2, true>(e)));
+        TRY((set_attr<M_F16X3, 1, false>(e))); TRY((set_attr<M_F16X3, 2, false>(e))); TRY((set_attr<M_F16X3, 2, true>(e)));
+        TRY((set_attr<M_F16F8, 1, false>(e))); TRY((set_attr<M_F16F8, 2, false>(e))); TRY((set_attr<M_F16F8, 2, true>(e)));
         s->attr_set = true;
     }
     *out = s;
@@ -498,33 +568,41 @@ int weight_map(dmp2_engine* e, CUtensorMap* map, const void* w, int rows, int K,
     return encode(e, map, w, elem_bytes, 2, dims, str, box);
 }
 
-template <int MODE, int CL>
+template <int MODE, int CL, bool PAIR>
 int launch(dmp2_engine* e, const ConvMaps& maps, const TcParams& p, int grid, cudaStream_t st) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(NUM_THREADS);
-    cfg.dynamicSmemBytes = Cfg<MODE>::SMEM_BYTES;
+    cfg.dynamicSmemBytes = Cfg<MODE, PAIR>::SMEM_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    CUDA_TRY(e, cudaLaunchKernelEx(&cfg, k_conv5_tc<MODE, CL>, maps, p));
+    CUDA_TRY(e, cudaLaunchKernelEx(&cfg, k_conv5_tc<MODE, CL, PAIR>, maps, p));
     POST_LAUNCH(e, "k_conv5_tc");
     return 0;
 }
 
-// persistent grid: one CTA per SM (or fewer when there is less work), a whole number of clusters
-int launch_mode(dmp2_engine* e, int mode, int cl, const ConvMaps& maps, TcParams& p, int row_tiles, cudaStream_t st) {
-    if (cl != 1) cl = 2;
+template <int MODE>
+int launch_form(dmp2_engine* e, int form, const ConvMaps& maps, const TcParams& p, int grid, cudaStream_t st) {
+    if (form == 0) return launch<MODE, 2, true>(e, maps, p, grid, st);
+    if (form == 2) return launch<MODE, 2, false>(e, maps, p, grid, st);
+    return launch<MODE, 1, false>(e, maps, p, grid, st);
+}
+
+// persistent grid: one CTA per SM (or fewer when there is less work), a whole number of clusters.
+// form: 0 = cta_group::2 CTA pairs (default), 1 = independent CTAs, 2 = cta_group::1 with 2-CTA weight multicast
+int launch_mode(dmp2_engine* e, int mode, int form, const ConvMaps& maps, TcParams& p, int row_tiles, cudaStream_t st) {
+    const int cl = form == 1 ? 1 : 2;
     p.units = cdiv(row_tiles, cl) * p.n_tiles_n;
     int sms = e->conv_sms > 0 ? std::min(e->conv_sms, e->num_sms) : e->num_sms;
     int grid = std::min(sms / cl, p.units) * cl;
     if (grid < cl) grid = cl;
-    if (mode == DMP2_CONV_TC_F16X3) return cl == 2 ? launch<M_F16X3, 2>(e, maps, p, grid, st) : launch<M_F16X3, 1>(e, maps, p, grid, st);
-    if (mode == DMP2_CONV_TC_F16F8) return cl == 2 ? launch<M_F16F8, 2>(e, maps, p, grid, st) : launch<M_F16F8, 1>(e, maps, p, grid, st);
-    return cl == 2 ? launch<M_F16, 2>(e, maps, p, grid, st) : launch<M_F16, 1>(e, maps, p, grid, st);
+    if (mode == DMP2_CONV_TC_F16X3) return launch_form<M_F16X3>(e, form, maps, p, grid, st);
+    if (mode == DMP2_CONV_TC_F16F8) return launch_form<M_F16F8>(e, form, maps, p, grid, st);
+    return launch_form<M_F16>(e, form, maps, p, grid, st);
 }
 
 }  // namespace
@@ -559,7 +637,7 @@ int run_conv_tc(dmp2_engine* e, int blk, const __half* xh, const __half* xl, con
     maps.a_hi = s->amap[0]; maps.a_lo = s->amap[1]; maps.a8_lo = s->amap[2]; maps.a8_hi = s->amap[3];
     maps.b_hi = s->wmap[blk][0]; maps.b_lo = s->wmap[blk][1]; maps.b8_w = s->wmap[blk][2]; maps.b8_lo = s->wmap[blk][3];
     TcParams p;
-    p.gemm = 0; p.L = L; p.H = H; p.y_off = y_off; p.tiles_x = cdiv(L, TILE_W); p.num_kb = 50; p.chunk_kb = 2;
+    p.gemm = 0; p.L = L; p.H = H; p.y_off = y_off; p.tiles_x = cdiv(L, TILE_W); p.num_kb = 50; p.chunk_kb = 2 * e->conv_chunk_taps;
     p.M = H * L; p.N = 512; p.n_tiles_n = 2; p.out = raw; p.bias = bw.bias;
     p.stat_part = nullptr; p.ticket = nullptr; p.norm = nullptr; p.gamma = nullptr; p.totals = nullptr; p.npix = 0;
     if (fuse_stats) {
@@ -610,7 +688,7 @@ int run_gemm_tn_test(dmp2_engine* e, const float* a, const float* b, int M, int 
         p.gemm = 1; p.L = 0; p.H = 0; p.y_off = 0; p.tiles_x = 1; p.num_kb = K / KCHUNK; p.chunk_kb = chunk_k / KCHUNK;
         p.M = M; p.N = N; p.n_tiles_n = cdiv(N, TILE_N); p.out = c; p.bias = nullptr;
         p.stat_part = nullptr; p.ticket = nullptr; p.norm = nullptr; p.gamma = nullptr; p.totals = nullptr; p.npix = 0;
-        rc = launch_mode(e, mode, 1, maps, p, cdiv(M, TILE_M), st);
+        rc = launch_mode(e, mode, e->conv_cluster, maps, p, cdiv(M, TILE_M), st);
     } while (0);
     cudaStreamSynchronize(st);
     cudaFree(ah); cudaFree(al); cudaFree(bh); cudaFree(bl);

@@ -427,6 +427,9 @@ int dmp2_create(dmp2_engine** out, int device, int n_tensors, const char* const*
     }
     const char* cc = getenv("DMP2_CONV_CLUSTER");
     if (cc && (!strcmp(cc, "1") || !strcmp(cc, "2"))) e->conv_cluster = atoi(cc);
+    if (cc && !strcmp(cc, "pair")) e->conv_cluster = 0;
+    const char* ck = getenv("DMP2_CONV_CHUNK");
+    if (ck && (atoi(ck) == 1 || atoi(ck) == 5 || atoi(ck) == 25)) e->conv_chunk_taps = atoi(ck);
     const char* cs = getenv("DMP2_CONV_SMS");
     if (cs && atoi(cs) > 0) e->conv_sms = atoi(cs);
     const char* vm = getenv("DMP2_VGRU");
@@ -485,7 +488,7 @@ int dmp2_set_profile(dmp2_engine* e, int on) {
     if (!e) return DMP2_ERR_BAD_ARG;
     TRY(check_device(e));
     if (on && e->prof_ev.empty()) {
-        e->prof_ev.resize(2 * DMP2_NBLOCKS * 128);
+        e->prof_ev.resize(2 * DMP2_NBLOCKS * 11 * 64);       // 64 folds of 10 recycles; beyond that launches go untimed
         for (auto& ev : e->prof_ev) CUDA_TRY(e, cudaEventCreate(&ev));
     }
     e->profile = on != 0;

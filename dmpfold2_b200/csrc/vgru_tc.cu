@@ -9,6 +9,8 @@
 // TMA -> smem ring -> tcgen05.mma (fp16 hi/lo split of both operands, 3 MMAs, fp32 accumulate in TMEM) ->
 // epilogue warps apply the GRU cell and write h as fp32 + fp16 hi/lo (the next step's A operand).
 // GRU weights do not tolerate single-pass fp16/tf32, hence the 3-term split.
+// The tcgen05 accumulator truncates on every MMA (see conv_tc.cu), so K = 512 is accumulated as FOUR chains of 24 MMAs
+// in four TMEM accumulators which the epilogue adds in fp32 with round-to-nearest.
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -17,6 +19,7 @@ using namespace tc;
 
 constexpr int VT_N = 96;                       // accumulator columns per CTA: 3 gates x 32 units
 constexpr int VT_NKB = 8;                      // K = 512 in chunks of 64
+constexpr int VT_NACC = 4;                     // accumulation chains (2 k-blocks each), 128 TMEM columns apart
 constexpr int VT_A_BYTES = 128 * 64 * 2;       // 16 KB
 constexpr int VT_B_BYTES = VT_N * 64 * 2;      // 12 KB
 constexpr int VT_STAGE_BYTES = 2 * VT_A_BYTES + 2 * VT_B_BYTES;     // 56 KB
@@ -85,7 +88,7 @@ __global__ void __launch_bounds__(VT_THREADS, 1) k_vgru_step(const __grid_consta
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(tmem_slot) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -133,11 +136,12 @@ __global__ void __launch_bounds__(VT_THREADS, 1) k_vgru_step(const __grid_consta
                 tc_fence_after();
                 const uint32_t a_hi = base + s * VT_STAGE_BYTES, a_lo = a_hi + VT_A_BYTES;
                 const uint32_t b_hi = a_hi + 2 * VT_A_BYTES, b_lo = b_hi + VT_B_BYTES;
+                const uint32_t d = tmem_base + (uint32_t)(kb >> 1) * 128u;        // chain kb/2
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
-                    tc_mma_f16(tmem_base, make_smem_desc(a_hi + k * 32), make_smem_desc(b_hi + k * 32), idesc, !(kb == 0 && k == 0));
-                    tc_mma_f16(tmem_base, make_smem_desc(a_lo + k * 32), make_smem_desc(b_hi + k * 32), idesc, 1u);
-                    tc_mma_f16(tmem_base, make_smem_desc(a_hi + k * 32), make_smem_desc(b_lo + k * 32), idesc, 1u);
+                    tc_mma_f16(d, make_smem_desc(a_hi + k * 32), make_smem_desc(b_hi + k * 32), idesc, !((kb & 1) == 0 && k == 0));
+                    tc_mma_f16(d, make_smem_desc(a_lo + k * 32), make_smem_desc(b_hi + k * 32), idesc, 1u);
+                    tc_mma_f16(d, make_smem_desc(a_hi + k * 32), make_smem_desc(b_lo + k * 32), idesc, 1u);
                 }
                 tc_commit(empty(s));
                 if (++s == VT_STAGES) { s = 0; ph ^= 1; }
@@ -169,10 +173,24 @@ __global__ void __launch_bounds__(VT_THREADS, 1) k_vgru_step(const __grid_consta
         mbar_wait(acc_full, 0);
         tc_fence_after();
         float ar[8], az[8], an[8];
-        tmem_ld8(lane_addr, ar);
-        tmem_ld8(lane_addr + 32, az);
-        tmem_ld8(lane_addr + 64, an);
-        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < VT_NACC; c += 2) {                 // two chains per round trip: (c0 + c1) + (c2 + c3)
+            float pr[2][8], pz[2][8], pn[2][8];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                tmem_ld8(lane_addr + (c + u) * 128, pr[u]);
+                tmem_ld8(lane_addr + (c + u) * 128 + 32, pz[u]);
+                tmem_ld8(lane_addr + (c + u) * 128 + 64, pn[u]);
+            }
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const float sr = pr[0][j] + pr[1][j], sz = pz[0][j] + pz[1][j], sn = pn[0][j] + pn[1][j];
+                ar[j] = c == 0 ? sr : ar[j] + sr;
+                az[j] = c == 0 ? sz : az[j] + sz;
+                an[j] = c == 0 ? sn : an[j] + sn;
+            }
+        }
         if (valid) {
 #pragma unroll
             for (int j = 0; j < 8; j++) {
@@ -210,7 +228,7 @@ __global__ void __launch_bounds__(VT_THREADS, 1) k_vgru_step(const __grid_consta
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem_base) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
     }
 }
 

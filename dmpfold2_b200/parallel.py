@@ -61,6 +61,73 @@ def fold_many(targets: Sequence, fold_fn: Callable[[object], object], gather: bo
     return [merged[t] for t in range(len(targets))]
 
 
+class StreamPool:
+    """Throughput mode on ONE GPU: K engines on K CUDA streams fold independent targets concurrently
+    (BASELINE.json configs[2]: "one target per stream").
+
+    A single fold is a serial chain in which the tensor-core conv owns the whole GPU ~2/3 of the time and the rest is
+    latency-bound (1000 dependent vgru steps, the eigensolver, the GRUs).  With K targets in flight the latency-bound
+    stages of one target run beside the convs of another.  Every engine has its own workspace; the weights are
+    uploaded once per engine.  `conv_sms` < #SMs keeps a few SMs free of the persistent conv kernel so that the small
+    kernels of the other streams never wait for a whole conv launch to drain.
+
+    engine_factory(i) -> engine lets the CPU tests (and other back ends) substitute the engine; an engine needs
+    fold(msa, template, iterations, minsteps) -> (coords, confs), set_conv_sms(n) and close().
+    """
+
+    def __init__(self, state_dict=None, device_index: int = 0, streams: int = 2, conv_mode: Optional[str] = None,
+                 conv_sms: int = 0, engine_factory: Optional[Callable[[int], object]] = None):
+        if streams < 1:
+            raise ValueError('streams must be >= 1')
+        if engine_factory is None:
+            from .engine import Engine
+
+            def engine_factory(i):
+                return Engine(state_dict, device_index, conv_mode=conv_mode)
+        self.device_index = device_index
+        self.engines = [engine_factory(i) for i in range(streams)]
+        if conv_sms:
+            for e in self.engines:
+                e.set_conv_sms(conv_sms)
+        self._streams = None
+
+    def _cuda_streams(self):
+        if self._streams is None:
+            dev = torch.device('cuda', self.device_index)
+            self._streams = [torch.cuda.Stream(device=dev) for _ in self.engines]
+        return self._streams
+
+    def assignment(self, num_targets: int) -> List[int]:
+        """Stream index of every target: round-robin, so consecutive targets are in flight together."""
+        return [t % len(self.engines) for t in range(num_targets)]
+
+    def fold_all(self, msas: Sequence, templates: Optional[Sequence] = None, iterations: int = 10, minsteps: int = 100,
+                 use_cuda_streams: bool = True) -> List[Tuple[object, object]]:
+        """Fold every alignment; returns [(coords, confs)] in input order.  Asynchronous w.r.t. the host until the
+        final synchronisation of the streams with the caller's current stream."""
+        k = len(self.engines)
+        out: List[Optional[Tuple[object, object]]] = [None] * len(msas)
+        if not use_cuda_streams:                     # (CPU tests / single-stream fallback of a custom engine)
+            for t, msa in enumerate(msas):
+                out[t] = self.engines[t % k].fold(msa, None if templates is None else templates[t], iterations, minsteps)
+            return out
+        streams = self._cuda_streams()
+        cur = torch.cuda.current_stream(torch.device('cuda', self.device_index))
+        for s in streams:
+            s.wait_stream(cur)
+        for t, msa in enumerate(msas):
+            with torch.cuda.stream(streams[t % k]):
+                out[t] = self.engines[t % k].fold(msa, None if templates is None else templates[t], iterations, minsteps)
+        for s in streams:
+            cur.wait_stream(s)
+        return out
+
+    def close(self):
+        for e in self.engines:
+            e.close()
+        self.engines = []
+
+
 def exchange_handles(handle: bytes) -> List[bytes]:
     """All-gather one small bytes object per rank, in rank order (works on gloo and NCCL groups)."""
     rank, ws = world()

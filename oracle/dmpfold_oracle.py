@@ -468,6 +468,31 @@ def synth_msa_structured(base: np.ndarray, length: int, nseqs: int, seed: int) -
     return msa
 
 
+def synth_msa_tandem(base: np.ndarray, length: int, nseqs: int, seed: int, mut: float = 0.02) -> np.ndarray:
+    """Tandem-repeat synthetic MSA: every column block reuses the SAME resampled rows of `base` (so the covariation
+    is consistent across the repeats) with `mut` point mutations; row 0 stays the (tiled) query."""
+    rng = np.random.default_rng(seed)
+    n0, l0 = base.shape
+    rows = np.concatenate(([0], rng.integers(1, n0, size=nseqs - 1)))
+    nblk = -(-length // l0)
+    msa = np.concatenate([base[rows]] * nblk, axis=1)[:, :length].copy()
+    m = rng.random(msa.shape) < mut
+    m[0] = False
+    msa[m] = rng.integers(0, 20, size=int(m.sum()), dtype=np.uint8)
+    return msa
+
+
+def synth_template_domains(domain_ca: np.ndarray, length: int, gap: float = 8.0) -> np.ndarray:
+    """Template CA trace for a tiled synthetic target: copies of one folded domain (e.g. the reference's own PF10963
+    prediction, tests/golden/pf10963_n10_m100.npz) laid out along x, `gap` Angstrom apart, cropped to `length` residues.
+    Seeding the recycling loop with it (predict.py:142-143) gives a confident, well-conditioned L=300 target."""
+    dom = np.asarray(domain_ca, dtype=np.float64)
+    span = dom.max(0) - dom.min(0)
+    ncopy = -(-length // len(dom))
+    tm = np.concatenate([dom + np.array([k * (span[0] + gap), 0.0, 0.0]) for k in range(ncopy)])[:length]
+    return tm.astype(np.float32)
+
+
 def kabsch_rmsd(a: np.ndarray, b: np.ndarray) -> float:
     """RMSD of two (L,3) point sets after optimal superposition."""
     a = np.asarray(a, dtype=np.float64)

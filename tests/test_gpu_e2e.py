@@ -146,22 +146,8 @@ def test_cfg5_size_single_gpu_properties(eng, pf10963):
     assert f0.min() >= 0.0 and f0.max() <= 1.0
 
 
-def test_cfg2_full_size_vs_oracle(eng, oracle, pf10963):
-    """The headline configuration itself (BASELINE.json configs[1]: L=300, N=1000) against the oracle, default conv mode.
-
-    One pass (n=0, m=0) must meet the 1e-3 A bar.  With 10 recycles + 100 minimiser steps this low-confidence
-    structured-synthetic target (mean conf 0.30) amplifies any perturbation ~10-16x through the recycling loop: the
-    oracle differs from ITSELF by 5.0e-4 A between 24 and 4 host threads, the fp32 CUDA-core conv path by 2.8e-3 A,
-    the default tensor-core path by 5.2e-3 A (profiles/round1_cfg2_parity_diag.txt).  The full-length run is therefore
-    held to 1e-2 A here (20x the reference's own irreproducibility) and the number is printed."""
-    msa = O.synth_msa_structured(pf10963, 300, 1000, 0)
-    eng.set_conv_mode('f16f8')
-    ref_c, ref_f = oracle.fold(msa, iterations=0, minsteps=0)
-    coords, conf = eng.fold_host(msa, None, 0, 0)
-    _check(coords, conf, {'coords': ref_c.numpy(), 'confs': ref_f.numpy()})
-    ref_c, ref_f = oracle.fold(msa, iterations=10, minsteps=100)
-    coords, conf = eng.fold_host(msa, None, 10, 100)
-    _check(coords, conf, {'coords': ref_c.numpy(), 'confs': ref_f.numpy()}, tol=1e-2)
+# (the headline configuration L=300 / N=1000 at its full 10 recycles + 100 minimiser steps, and the other full-length
+#  BASELINE.json shapes, are checked in tests/test_gpu_parity_r2.py against fp32 + fp64 fixtures of the reference algorithm)
 
 
 @pytest.mark.parametrize('l,n', [(8, 2), (9, 1), (17, 3)])
@@ -170,9 +156,9 @@ def test_minimal_sizes_vs_oracle(eng, oracle, pf10963, l, n):
     branch (predict.py:139)."""
     msa = np.ascontiguousarray(pf10963[:n, 20:20 + l])
     ref_c, ref_f = oracle.fold(msa, iterations=1, minsteps=5)
-    eng.set_conv_mode('f16f8')
+    eng.set_conv_mode('f16x3')
     coords, conf = eng.fold_host(msa, None, 1, 5)
-    _check(coords, conf, {'coords': ref_c.numpy(), 'confs': ref_f.numpy()}, tol=2e-3)
+    _check(coords, conf, {'coords': ref_c.numpy(), 'confs': ref_f.numpy()})
 
 
 @needs_weights

@@ -25,6 +25,34 @@ def test_round_robin_shards_partition_the_targets():
     assert P.exchange_handles(b'x' * 64) == [b'x' * 64]
 
 
+def test_stream_pool_host_logic():
+    """StreamPool: round-robin stream assignment, per-engine SM carve-out, results in input order (engine stand-in)."""
+    class Fake:
+        def __init__(self, i):
+            self.i, self.sms, self.seen, self.closed = i, None, [], False
+
+        def set_conv_sms(self, n):
+            self.sms = n
+
+        def fold(self, msa, tmpl, n, m):
+            self.seen.append((msa, tmpl, n, m))
+            return ('coords%d' % msa, 'eng%d' % self.i)
+
+        def close(self):
+            self.closed = True
+    pool = P.StreamPool(streams=3, conv_sms=132, engine_factory=Fake)
+    engines = list(pool.engines)
+    assert [e.sms for e in engines] == [132, 132, 132]
+    assert pool.assignment(7) == [0, 1, 2, 0, 1, 2, 0]
+    res = pool.fold_all(list(range(7)), templates=['t%d' % i for i in range(7)], iterations=2, minsteps=5, use_cuda_streams=False)
+    assert res == [('coords%d' % t, 'eng%d' % (t % 3)) for t in range(7)]
+    assert engines[1].seen == [(1, 't1', 2, 5), (4, 't4', 2, 5)]
+    pool.close()
+    assert all(e.closed for e in engines) and pool.engines == []
+    with pytest.raises(ValueError):
+        P.StreamPool(streams=0, engine_factory=Fake)
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(('127.0.0.1', 0))

@@ -12,7 +12,9 @@ algorithm, pinned against /root/reference by oracle/make_golden.py) three times 
 and writes a small fixture (coords/confs of all three + the generator arguments) to tests/golden/.  The GPU tests
 compare the engine with ref32 (the bar) and report its distance to ref64 beside the reference's.
 
-    python tools/fp64_triangulate.py NAME L N SEED n m [generator]
+    python tools/fp64_triangulate.py NAME L N SEED n m [generator] [template]
+
+template = "domains": seed the fold with copies of the reference's PF10963 prediction (O.synth_template_domains).
 """
 import os
 import sys
@@ -37,11 +39,16 @@ def make_msa(gen, base, L, N, seed):
 def main():
     name, L, N, seed, n, m = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]), int(sys.argv[6])
     gen = sys.argv[7] if len(sys.argv) > 7 else 'structured'
+    tmpl_kind = sys.argv[8] if len(sys.argv) > 8 else 'none'
     wdir = os.path.join(ROOT, 'dmpfold2_b200', 'trained_model')
     sd = O.load_state_dict(wdir)
     base = O.encode_aln(O.read_aln(os.path.join(ROOT, 'tests', 'golden', 'PF10963.aln')))
     msa = make_msa(gen, base, L, N, seed)
-    out = {'L': L, 'N': N, 'seed': seed, 'iterations': n, 'minsteps': m, 'generator': gen,
+    tmpl = None
+    if tmpl_kind == 'domains':
+        dom = np.load(os.path.join(ROOT, 'tests', 'golden', 'pf10963_n10_m100.npz'))['coords'][:, 1]
+        tmpl = O.synth_template_domains(dom, L)
+    out = {'L': L, 'N': N, 'seed': seed, 'iterations': n, 'minsteps': m, 'generator': gen, 'template': tmpl_kind,
            'torch': torch.__version__, 'threads': torch.get_num_threads()}
 
     def rmsd(a, b):
@@ -50,13 +57,13 @@ def main():
     orc = O.Oracle(sd)
     for tag, nm in (('ref32', (n, m)), ('ref32_pass', (0, 0))):
         t = time.time()
-        c, f = orc.fold(msa, iterations=nm[0], minsteps=nm[1])
+        c, f = orc.fold(msa, template_ca=tmpl, iterations=nm[0], minsteps=nm[1])
         out[tag + '_coords'], out[tag + '_confs'] = c.numpy(), f.numpy()
         print(tag, nm, 'time %.1fs mean conf %.4f' % (time.time() - t, float(f.mean())), flush=True)
     nthr = torch.get_num_threads()
     torch.set_num_threads(4 if nthr != 4 else 3)
     for tag, nm in (('ref32_alt', (n, m)), ('ref32_alt_pass', (0, 0))):
-        c, f = orc.fold(msa, iterations=nm[0], minsteps=nm[1])
+        c, f = orc.fold(msa, template_ca=tmpl, iterations=nm[0], minsteps=nm[1])
         out[tag + '_coords'], out[tag + '_confs'] = c.numpy(), f.numpy()
     torch.set_num_threads(nthr)
     print('self-noise  %d/%d: %.3e A   0/0: %.3e A' % (n, m, rmsd(out['ref32_coords'], out['ref32_alt_coords']),
@@ -64,7 +71,7 @@ def main():
     orc64 = O.Oracle(sd, dtype=torch.float64)
     for tag, nm in (('ref64_pass', (0, 0)), ('ref64', (n, m))):
         t = time.time()
-        c, f = orc64.fold(msa, iterations=nm[0], minsteps=nm[1])
+        c, f = orc64.fold(msa, template_ca=tmpl, iterations=nm[0], minsteps=nm[1])
         out[tag + '_coords'], out[tag + '_confs'] = c.numpy(), f.numpy()
         print(tag, nm, 'time %.1fs mean conf %.4f' % (time.time() - t, float(f.mean())), flush=True)
     print('fp32 vs fp64  %d/%d: %.3e A (alt threads %.3e)   0/0: %.3e A (alt %.3e)' % (
