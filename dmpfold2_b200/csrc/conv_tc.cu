@@ -11,7 +11,7 @@
 // (cta_group::1 forms with or without TMA multicast of the weights are kept as validation variants.)
 //
 //   warp 0       TMA producer: cp.async.bulk.tensor (128B swizzle; out-of-bounds zero fill = the pad-2 border) into an
-//                A ring (shifted pixel patch) and a B ring (256-cout weight pieces, multicast across a CTA cluster)
+//                ring of k-block stages (shifted pixel patch + the 256-cout weight pieces of that k-block)
 //   warp 1       TMEM allocator + single-thread tcgen05.mma issuer, M=128 N=256
 //   warps 2..3   idle (they complete the first warpgroup, which gives its registers away: setmaxnreg 56)
 //   warps 4..11  epilogue (two warpgroups, setmaxnreg 224): drain tensor memory into registers
@@ -51,14 +51,15 @@ constexpr int FIRST_EPI_WARP = 4;
 constexpr int NUM_THREADS = (FIRST_EPI_WARP + NUM_EPI_WARPS) * 32;
 enum { M_F16 = 0, M_F16X3 = 1, M_F16F8 = 2 };
 
+// One ring of k-block stages: [A operand tiles | B pieces], one full / empty mbarrier pair per stage.
 template <int MODE, bool PAIR>
 struct Cfg {
     static constexpr int A_STAGE_BYTES = MODE == M_F16 ? A_BYTES : 2 * A_BYTES;
-    static constexpr int NUM_A_STAGES = PAIR ? (MODE == M_F16 ? 6 : 3) : (MODE == M_F16 ? 4 : 2);
     static constexpr int PIECES = MODE == M_F16 ? 1 : 2;      // B pieces per k-block
     static constexpr int B_SLOT_BYTES = PAIR ? B_BYTES / 2 : B_BYTES;     // a CTA of a pair holds 128 of the piece's 256 couts
-    static constexpr int NUM_B_SLOTS = PAIR ? 8 : 5;
-    static constexpr int SMEM_BYTES = NUM_A_STAGES * A_STAGE_BYTES + NUM_B_SLOTS * B_SLOT_BYTES + 1024 /*align*/ + 512 /*barriers*/;
+    static constexpr int STAGE_BYTES = A_STAGE_BYTES + PIECES * B_SLOT_BYTES;
+    static constexpr int NUM_STAGES = (224 * 1024) / STAGE_BYTES;        // pair: 3 (f16x3, f16f8) / 7 (f16); else 2 / 4
+    static constexpr int SMEM_BYTES = NUM_STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 struct ConvMaps {
@@ -171,21 +172,17 @@ __device__ __forceinline__ Unit decode_unit(const TcParams& p, int cu, uint32_t 
 template <int MODE, int CL, bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv5_tc(const __grid_constant__ ConvMaps maps, const TcParams p) {
     using C = Cfg<MODE, PAIR>;
-    constexpr int NUM_B_SLOTS = C::NUM_B_SLOTS;
+    constexpr int NS = C::NUM_STAGES;
     constexpr int B_SLOT = C::B_SLOT_BYTES;
     static_assert(!PAIR || CL == 2, "a CTA pair is a cluster of two");
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // 128B swizzle needs 1024-byte alignment
-    const uint32_t a_base = base;
-    const uint32_t b_base = base + C::NUM_A_STAGES * C::A_STAGE_BYTES;
-    const uint32_t bar_base = b_base + NUM_B_SLOTS * B_SLOT;
-    auto a_full = [&](int s) { return bar_base + 8u * s; };
-    auto a_empty = [&](int s) { return bar_base + 8u * (C::NUM_A_STAGES + s); };
-    auto b_full = [&](int s) { return bar_base + 8u * (2 * C::NUM_A_STAGES + s); };
-    auto b_empty = [&](int s) { return bar_base + 8u * (2 * C::NUM_A_STAGES + NUM_B_SLOTS + s); };
-    auto c_full = [&](int s) { return bar_base + 8u * (2 * C::NUM_A_STAGES + 2 * NUM_B_SLOTS + s); };
-    auto c_empty = [&](int s) { return bar_base + 8u * (2 * C::NUM_A_STAGES + 2 * NUM_B_SLOTS + 2 + s); };
-    const uint32_t tmem_slot = bar_base + 8u * (2 * C::NUM_A_STAGES + 2 * NUM_B_SLOTS + 4);
+    const uint32_t bar_base = base + NS * C::STAGE_BYTES;
+    auto full = [&](int s) { return bar_base + 8u * s; };
+    auto empty = [&](int s) { return bar_base + 8u * (NS + s); };
+    auto c_full = [&](int s) { return bar_base + 8u * (2 * NS + s); };
+    auto c_empty = [&](int s) { return bar_base + 8u * (2 * NS + 2 + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * NS + 4);
     uint8_t* smem_gen = smem_raw + (base - smem_u32(smem_raw));
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - base));
 
@@ -197,8 +194,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv5_tc(const __grid_consta
     const int chunks_per_unit = p.num_kb / p.chunk_kb;
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < C::NUM_A_STAGES; s++) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
-        for (int s = 0; s < NUM_B_SLOTS; s++) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), PAIR ? 1 : CL); }
+        // a stage is free when every CTA that delivers into it (weight multicast) has finished reading it
+        for (int s = 0; s < NS; s++) { mbar_init(full(s), 1); mbar_init(empty(s), PAIR ? 1 : CL); }
         // pair: the leader's issuer waits for the epilogue warps of BOTH CTAs before it reuses a chunk accumulator
         for (int s = 0; s < 2; s++) { mbar_init(c_full(s), 1); mbar_init(c_empty(s), PAIR ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -228,11 +225,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv5_tc(const __grid_consta
     if (warp == 0) {
         // ===================== TMA producer (whole warp, one elected lane issues) =====================
         {
-            int sa = 0, pa = 0, sb = 0, pb = 0;
+            int st = 0, ph = 0;
             for (int cu = cluster_id; cu < p.units; cu += num_clusters) {
                 const Unit u = decode_unit<CL>(p, cu, crank);
                 for (int kb = 0; kb < p.num_kb; kb++) {
-                    // ---- A stage
                     const int tap = kb >> 1, sub = kb & 1;
                     int c1, c2;
                     if (p.gemm) { c1 = u.m0; c2 = 0; }
@@ -240,66 +236,59 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv5_tc(const __grid_consta
                         const int dy = tap / 5, dx = tap - dy * 5;
                         c1 = u.x0 + dx - 2; c2 = u.y0 + dy - 2 + p.y_off;
                     }
-                    mbar_wait(a_empty(sa), pa ^ 1);
+                    mbar_wait(empty(st), ph ^ 1);
                     // pair: the loads of both CTAs signal the LEADER's barrier, which expects the bytes of both
-                    const uint32_t afl = PAIR ? mapa_u32(a_full(sa), 0) : a_full(sa);
-                    const uint32_t ast = a_base + sa * C::A_STAGE_BYTES;
+                    const uint32_t fl = PAIR ? mapa_u32(full(st), 0) : full(st);
+                    const uint32_t ast = base + st * C::STAGE_BYTES;
+                    const uint32_t bst = ast + C::A_STAGE_BYTES;
                     if (elect_one()) {
-                    if (!PAIR) mbar_expect_tx(a_full(sa), C::A_STAGE_BYTES);
-                    else if (leader) mbar_expect_tx(a_full(sa), 2 * C::A_STAGE_BYTES);
-                    auto load_a = [&](uint32_t dst, const CUtensorMap* m, int c0) {
-                        if (PAIR) tma2_load_3d(dst, m, afl, c0, c1, c2);
-                        else tma_load_3d(dst, m, afl, c0, c1, c2);
-                    };
-                    if (MODE == M_F16) {
-                        load_a(ast, &maps.a_hi, p.gemm ? kb * KCHUNK : sub * KCHUNK);
-                    } else if (MODE == M_F16X3) {
-                        const int c0 = p.gemm ? kb * KCHUNK : sub * KCHUNK;
-                        load_a(ast, &maps.a_hi, c0);
-                        load_a(ast + A_BYTES, &maps.a_lo, c0);
-                    } else if (sub == 0) {                         // F16F8: the two fp8 correction operands (128 channels each)
-                        load_a(ast, &maps.a8_lo, 0);
-                        load_a(ast + A_BYTES, &maps.a8_hi, 0);
-                    } else {                                       // F16F8: both fp16 channel chunks of x_hi
-                        load_a(ast, &maps.a_hi, 0);
-                        load_a(ast + A_BYTES, &maps.a_hi, KCHUNK);
-                    }
-                    }
-                    __syncwarp();
-                    if (++sa == C::NUM_A_STAGES) { sa = 0; pa ^= 1; }
-                    // ---- B pieces
-                    for (int piece = 0; piece < C::PIECES; piece++) {
-                        const CUtensorMap* bm;
-                        int k0;                                    // element offset along K of the weight row
-                        if (MODE == M_F16F8) {
-                            if (sub == 0) { bm = piece ? &maps.b8_lo : &maps.b8_w; k0 = tap * 128; }
-                            else { bm = &maps.b_hi; k0 = tap * 128 + piece * KCHUNK; }
-                        } else {
-                            bm = piece == 0 ? &maps.b_hi : &maps.b_lo;
-                            k0 = kb * KCHUNK;                      // weights are [512][K] with k = tap*128 + c = kb*64 + ...
+                        if (!PAIR) mbar_expect_tx(full(st), C::A_STAGE_BYTES + C::PIECES * B_BYTES);
+                        else if (leader) mbar_expect_tx(full(st), 2 * C::STAGE_BYTES);
+                        auto load_a = [&](uint32_t dst, const CUtensorMap* m, int c0) {
+                            if (PAIR) tma2_load_3d(dst, m, fl, c0, c1, c2);
+                            else tma_load_3d(dst, m, fl, c0, c1, c2);
+                        };
+                        if (MODE == M_F16) {
+                            load_a(ast, &maps.a_hi, p.gemm ? kb * KCHUNK : sub * KCHUNK);
+                        } else if (MODE == M_F16X3) {
+                            const int c0 = p.gemm ? kb * KCHUNK : sub * KCHUNK;
+                            load_a(ast, &maps.a_hi, c0);
+                            load_a(ast + A_BYTES, &maps.a_lo, c0);
+                        } else if (sub == 0) {                     // F16F8: the two fp8 correction operands (128 channels each)
+                            load_a(ast, &maps.a8_lo, 0);
+                            load_a(ast + A_BYTES, &maps.a8_hi, 0);
+                        } else {                                   // F16F8: both fp16 channel chunks of x_hi
+                            load_a(ast, &maps.a_hi, 0);
+                            load_a(ast + A_BYTES, &maps.a_hi, KCHUNK);
                         }
-                        mbar_wait(b_empty(sb), pb ^ 1);
-                        const uint32_t bdst = b_base + sb * B_SLOT;
-                        if (elect_one()) {
-                        if (PAIR) {                                // my 128 couts of the piece, as two 64-row boxes
-                            const uint32_t bfl = mapa_u32(b_full(sb), 0);
-                            if (leader) mbar_expect_tx(b_full(sb), 2 * B_SLOT);
-                            const int nr = u.n0 + (int)crank * 128;
-                            tma2_load_2d(bdst, bm, bfl, k0, nr);
-                            tma2_load_2d(bdst + BQ_BYTES, bm, bfl, k0, nr + BQ_ROWS);
-                        } else {
-                            mbar_expect_tx(b_full(sb), B_BYTES);
 #pragma unroll
-                            for (int i = 0; i < 4 / CL; i++) {     // my quarters of the piece, delivered to every CTA of the cluster
-                                const int qd = crank * (4 / CL) + i;
-                                if (CL == 1) tma_load_2d(bdst + qd * BQ_BYTES, bm, b_full(sb), k0, u.n0 + qd * BQ_ROWS);
-                                else tma_load_2d_mc(bdst + qd * BQ_BYTES, bm, b_full(sb), k0, u.n0 + qd * BQ_ROWS, MC_MASK);
+                        for (int piece = 0; piece < C::PIECES; piece++) {
+                            const CUtensorMap* bm;
+                            int k0;                                // element offset along K of the weight row
+                            if (MODE == M_F16F8) {
+                                if (sub == 0) { bm = piece ? &maps.b8_lo : &maps.b8_w; k0 = tap * 128; }
+                                else { bm = &maps.b_hi; k0 = tap * 128 + piece * KCHUNK; }
+                            } else {
+                                bm = piece == 0 ? &maps.b_hi : &maps.b_lo;
+                                k0 = kb * KCHUNK;                  // weights are [512][K] with k = tap*128 + c = kb*64 + ...
+                            }
+                            const uint32_t bdst = bst + piece * B_SLOT;
+                            if (PAIR) {                            // my 128 couts of the piece, as two 64-row boxes
+                                const int nr = u.n0 + (int)crank * 128;
+                                tma2_load_2d(bdst, bm, fl, k0, nr);
+                                tma2_load_2d(bdst + BQ_BYTES, bm, fl, k0, nr + BQ_ROWS);
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 4 / CL; i++) { // my quarters of the piece, delivered to every CTA of the cluster
+                                    const int qd = crank * (4 / CL) + i;
+                                    if (CL == 1) tma_load_2d(bdst + qd * BQ_BYTES, bm, fl, k0, u.n0 + qd * BQ_ROWS);
+                                    else tma_load_2d_mc(bdst + qd * BQ_BYTES, bm, fl, k0, u.n0 + qd * BQ_ROWS, MC_MASK);
+                                }
                             }
                         }
-                        }
-                        __syncwarp();
-                        if (++sb == NUM_B_SLOTS) { sb = 0; pb ^= 1; }
                     }
+                    __syncwarp();
+                    if (++st == NS) { st = 0; ph ^= 1; }
                 }
             }
         }
@@ -328,46 +317,34 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv5_tc(const __grid_consta
                 else if (shared_slot && CL > 1) tc_commit_mc(bar, MC_MASK);
                 else tc_commit(bar);
             };
-            int sa = 0, pa = 0, sb = 0, pb = 0;
+            int st = 0, ph = 0;
             uint32_t cc = 0;                                      // chunk counter over the whole kernel: buffer cc & 1
             for (int cu = cluster_id; cu < p.units; cu += num_clusters) {
                 for (int kb = 0; kb < p.num_kb; kb++) {
                     const int sub = kb & 1;
                     const int in_chunk = kb % p.chunk_kb;
                     const uint32_t cs = cc & 1u;
-                    if (in_chunk == 0) {                           // the epilogue must have drained this chunk accumulator
-                        mbar_wait(c_empty(cs), ((cc >> 1) & 1u) ^ 1u);
-                        tc_fence_after();
-                    }
+                    if (in_chunk == 0) mbar_wait(c_empty(cs), ((cc >> 1) & 1u) ^ 1u);   // the epilogue has drained this chunk accumulator
                     const uint32_t d = tmem_base + cs * (uint32_t)TILE_N;
-                    mbar_wait(a_full(sa), pa);
-                    const uint64_t da0 = make_smem_desc(a_base + sa * C::A_STAGE_BYTES);
-                    const uint64_t da1 = make_smem_desc(a_base + sa * C::A_STAGE_BYTES + A_BYTES);
-#pragma unroll
-                    for (int piece = 0; piece < C::PIECES; piece++) {
-                        mbar_wait(b_full(sb), pb);
-                        tc_fence_after();
-                        const uint64_t db = make_smem_desc(b_base + sb * B_SLOT);
-                        const bool first = in_chunk == 0 && piece == 0;               // first MMA of the chain overwrites
-                        if (elect_one()) {
-                            if (MODE == M_F16F8) {
-                                if (sub == 0) mma8x4(d, piece ? da1 : da0, db, first);   // corrections first (K = 32 fp8 per MMA)
-                                else mma16x4(d, piece ? da1 : da0, db, first);
-                            } else {
-                                mma16x4(d, da0, db, first);                            // piece 0: hi(A) x hi(B); piece 1: hi(A) x lo(B)
-                                if (MODE == M_F16X3 && piece == 0) mma16x4(d, da1, db, false);   // lo(A) x hi(B)
-                            }
-                            commit(b_empty(sb), true);             // the slot is free only when every CTA of the cluster is done with it
-                        }
-                        __syncwarp();
-                        if (++sb == NUM_B_SLOTS) { sb = 0; pb ^= 1; }
-                    }
+                    mbar_wait(full(st), ph);
+                    tc_fence_after();
+                    const uint32_t ast = base + st * C::STAGE_BYTES;
+                    const uint64_t da0 = make_smem_desc(ast), da1 = make_smem_desc(ast + A_BYTES);
+                    const uint64_t db0 = make_smem_desc(ast + C::A_STAGE_BYTES), db1 = make_smem_desc(ast + C::A_STAGE_BYTES + B_SLOT);
+                    const bool first = in_chunk == 0;                                   // first MMA of the chain overwrites
                     if (elect_one()) {
-                        commit(a_empty(sa), false);
-                        if (in_chunk == p.chunk_kb - 1) commit(c_full(cs), false);    // chain finished: hand it to the epilogue
+                        if (MODE == M_F16F8) {
+                            if (sub == 0) { mma8x4(d, da0, db0, first); mma8x4(d, da1, db1, false); }   // corrections first (K = 32 fp8 per MMA)
+                            else { mma16x4(d, da0, db0, first); mma16x4(d, da1, db1, false); }
+                        } else {
+                            mma16x4(d, da0, db0, first);                                // hi(A) x hi(B)
+                            if (MODE == M_F16X3) { mma16x4(d, da1, db0, false); mma16x4(d, da0, db1, false); }   // lo x hi, hi x lo
+                        }
+                        commit(empty(st), true);                   // the stage is free when every CTA of the cluster is done with it
+                        if (in_chunk == p.chunk_kb - 1) commit(c_full(cs), false);      // chain finished: hand it to the epilogue
                     }
                     __syncwarp();
-                    if (++sa == C::NUM_A_STAGES) { sa = 0; pa ^= 1; }
+                    if (++st == NS) { st = 0; ph ^= 1; }
                     if (in_chunk == p.chunk_kb - 1) cc++;
                 }
             }

@@ -659,8 +659,11 @@ int run_eig_top8(dmp2_engine* e, const float* m, int L, float* vals, float* mds_
     int r8, v8, r16, v16;
     size_t s8, s16;
     plan(8, r8, v8, s8);
-    static const bool force16 = getenv("DMP2_EIG_CL") && atoi(getenv("DMP2_EIG_CL")) == 16;   // tuning knob
-    if (r8 && !force16) return launch_eig<8>(e, m, L, r8, v8, 0, s8, vals, mds_scaled, vecs_raw, st);
+    // With the fused sweep the column time is compute-bound, so from L ~ 200 on the 16-CTA cluster is faster even though
+    // the rows would fit 8 CTAs (L=300: 1.34 vs 1.46 ms, profiles/round1_eig_cl16_L300.txt).  DMP2_EIG_CL=8|16 forces one.
+    static const int force_cl = getenv("DMP2_EIG_CL") ? atoi(getenv("DMP2_EIG_CL")) : 0;      // tuning knob
+    const bool prefer16 = force_cl == 16 || (force_cl != 8 && L >= 200 && !e->eig_no_cl16);
+    if (r8 && !prefer16) return launch_eig<8>(e, m, L, r8, v8, 0, s8, vals, mds_scaled, vecs_raw, st);
     plan(16, r16, v16, s16);
     // rows do not even fit a 16-CTA cluster: tridiagonalise on the whole GPU, then phases 2-5 in one CTA
     static const bool no_grid = getenv("DMP2_EIG_GRID") && atoi(getenv("DMP2_EIG_GRID")) == 0;       // tuning knob

@@ -32,22 +32,41 @@ default_minsteps = 100
 MAX_SEQS = 3000                                     # predict.py:130-132
 _AA_TRANS = str.maketrans('ARNDCQEGHILKMFPSTWYVBJOUXZ-.', 'ABCDEFGHIJKLMNOPQRSTUUUUUUVV')   # predict.py:124
 
-_ENGINES: Dict[Tuple[str, int], Engine] = {}
+_ENGINES: Dict[Tuple[str, int, int], Engine] = {}
 
 
 def default_weights_dir() -> str:
     return os.environ.get('DMPFOLD_WEIGHTS_DIR', os.path.join(os.path.dirname(os.path.realpath(__file__)), 'trained_model'))
 
 
+MODEL_URL = 'https://github.com/psipred/DMPfold2/raw/master/dmpfold/trained_model/FINAL_fullmap_e2e_model_part{part}.pt'
+
+
+def download_trained_model(modeldir: str) -> None:
+    """predict.py:64-71 -- first-time download of the two weight parts (~140 MB) into `modeldir`."""
+    from urllib import request
+    print('Downloading trained model (~140 MB) as first time setup to ', modeldir, ', internet connection required',
+          sep='', file=sys.stderr)
+    if not os.path.isdir(modeldir):
+        os.mkdir(modeldir)
+    for part in ['1', '2']:
+        request.urlretrieve(MODEL_URL.format(part=part), os.path.join(modeldir, f'FINAL_fullmap_e2e_model_part{part}.pt'))
+
+
 def load_weights(weights_file: Optional[str] = None) -> Dict[str, torch.Tensor]:
-    """predict.py:83-96 -- two-part default weights merged by dict.update, or one custom file (-w)."""
+    """predict.py:83-96 -- two-part default weights merged by dict.update, or one custom file (-w); downloaded on
+    first use like the reference does when they are not there yet."""
     if weights_file is None:
         d = default_weights_dir()
         p1 = os.path.join(d, 'FINAL_fullmap_e2e_model_part1.pt')
         p2 = os.path.join(d, 'FINAL_fullmap_e2e_model_part2.pt')
         if not os.path.isfile(p1) or not os.path.isfile(p2):
-            raise FileNotFoundError(f'trained model not found in {d} (expected FINAL_fullmap_e2e_model_part[12].pt); '
-                                    'set DMPFOLD_WEIGHTS_DIR or pass weights_file')
+            try:
+                download_trained_model(d)
+            except Exception as ex:
+                raise FileNotFoundError(f'trained model not found in {d} (expected FINAL_fullmap_e2e_model_part[12].pt) and the '
+                                        f'download failed ({ex}); copy the two files there, set DMPFOLD_WEIGHTS_DIR or pass '
+                                        'weights_file') from ex
         sd = torch.load(p1, map_location='cpu')
         sd.update(torch.load(p2, map_location='cpu'))
         return sd
@@ -55,7 +74,10 @@ def load_weights(weights_file: Optional[str] = None) -> Dict[str, torch.Tensor]:
 
 
 def get_engine(weights_file: Optional[str], device_index: int) -> Engine:
-    key = (os.path.realpath(weights_file) if weights_file else '<default>', device_index)
+    """One engine per (weights, device, CUDA stream): an engine owns ONE workspace and its folds are asynchronous on the
+    caller's current stream, so callers on different streams (or threads with their own streams) must not share one."""
+    stream = torch.cuda.current_stream(torch.device('cuda', device_index)).cuda_stream if torch.cuda.is_available() else 0
+    key = (os.path.realpath(weights_file) if weights_file else '<default>', device_index, int(stream))
     eng = _ENGINES.get(key)
     if eng is None:
         eng = Engine(load_weights(weights_file), device_index)

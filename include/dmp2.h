@@ -45,11 +45,12 @@ typedef enum {
 /* Convolution arithmetic of the sixteen 5x5 ResNet blocks (network.py:26 inside ResNet_Block). */
 typedef enum {
     DMP2_CONV_TC_F16X3 = 0, /* tcgen05, fp16 hi+lo split of both operands, 3 MMAs per MAC, per-tap accumulation chains
-                               summed in fp32 registers: as accurate as an fp32 CPU conv (parity mode)           */
-    DMP2_CONV_TC_F16 = 1,   /* tcgen05, single fp16 MMA (informational; ~1e-4 relative operand error)            */
+                               summed in fp32 registers: per-block error equal to an fp32 CPU conv's            */
+    DMP2_CONV_TC_F16 = 1,   /* tcgen05, single fp16 MMA (informational; ~1e-4 relative operand error, fails parity) */
     DMP2_CONV_FFMA = 2,     /* CUDA-core fp32 implicit GEMM (validation path for the tensor-core kernels)        */
     DMP2_CONV_TC_F16F8 = 3  /* tcgen05, fp16 main term + the two hi/lo correction terms in FP8 (e4m3 x e5m2): 2 MMA-
-                               equivalents per MAC, operand error ~6e-6 relative (fast mode)                     */
+                               equivalents per MAC, same per-tap chains; the default -- whole folds end closer to the
+                               fp64 evaluation than the fp32 reference does (tests/test_gpu_parity_r2.py)        */
 } dmp2_conv_mode;
 
 /* ---- lifetime ------------------------------------------------------------------------------------ */

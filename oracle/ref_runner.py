@@ -38,11 +38,18 @@ def load():
     if not available():
         raise RuntimeError('oracle/_ref is missing: run `python oracle/make_ref.py` in the build container')
     _install_shim()
-    if REF_DIR not in sys.path:
-        sys.path.insert(0, REF_DIR)
-    import dmpfold
-    assert os.path.realpath(dmpfold.__file__).startswith(os.path.realpath(REF_DIR)), dmpfold.__file__
-    return dmpfold
+    # loaded under its own module name: the repository also ships a `dmpfold` alias package for the B200 engine
+    import importlib.util
+    if 'dmpfold_reference' in sys.modules:
+        return sys.modules['dmpfold_reference']
+    pkg = os.path.join(REF_DIR, 'dmpfold')
+    spec = importlib.util.spec_from_file_location('dmpfold_reference', os.path.join(pkg, '__init__.py'),
+                                                  submodule_search_locations=[pkg])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules['dmpfold_reference'] = mod
+    spec.loader.exec_module(mod)
+    assert os.path.realpath(mod.__file__).startswith(os.path.realpath(REF_DIR)), mod.__file__
+    return mod
 
 
 def merged_weights_file() -> str:

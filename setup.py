@@ -32,7 +32,7 @@ setuptools.setup(
                 'dmpfold CLI and dmpfold.aln_to_coords()',
     long_description=long_description,
     long_description_content_type='text/markdown',
-    packages=['dmpfold2_b200'],
+    packages=['dmpfold2_b200', 'dmpfold'],             # `dmpfold` = import-name alias of the reference package
     package_data={'dmpfold2_b200': ['libdmp2.so', 'csrc/*.cu', 'csrc/*.cuh', 'trained_model/*.pt']},
     scripts=['bin/dmpfold'],
     install_requires=['numpy', 'torch'],
