@@ -15,6 +15,9 @@
 #define DMP2_NBLOCKS 16
 #define DMP2_FEAT_LD 444     // 441 DCA + 1 APC + 2 zero pad (float4-aligned rows)
 #define DMP2_STEM_K (512 + DMP2_FEAT_LD)
+#define DMP2_STEM_KP 1024     // K of the stem GEMM padded to whole 128-element accumulation chains (tensor-core path)
+#define DMP2_STEM_SW 256.0f   // power-of-two scale of the stem weights in their fp16 hi/lo copies
+#define DMP2_TC_SLAB 32768    // rows of a GEMM A operand staged at a time in ws.tc_scratch
 
 struct Launch {              // per-engine launch bookkeeping (gpu_launches) + sticky error
     int64_t count = 0;
@@ -93,6 +96,8 @@ struct Weights {
     BiGruLayer cgru[3];
     float* coord_fc;         // [3][512]
     float* stem_w;           // [384][DMP2_STEM_K]  cols 0..511 outer, 512..953 DCA+APC, pad 0
+    __half* stem_w_hi;       // [384][DMP2_STEM_KP] fp16 hi/lo split of stem_w * DMP2_STEM_SW (tensor-core stem GEMM)
+    __half* stem_w_lo;
     float* stem_b;           // [384]
     float* stem_wd;          // [384]  weight of input channel 954 (the recycled distance map)
     float* stem_gamma;       // [128]
@@ -135,6 +140,9 @@ struct Workspace {
     float* dmap = nullptr;         // [L*L]
     float* base384 = nullptr;      // [L*L][384] cached stem pre-activation without the dmap term
     float* raw = nullptr;          // [L*L][128] maxout output before InstanceNorm
+    __half* tc_scratch = nullptr;  // operand staging of the tensor-core GEMMs: 4 x [DMP2_TC_SLAB][1024] fp16
+    __half* dca_tc = nullptr;      // fp16 hi/lo operands of the MSA-feature GEMMs (sized for (L, N))
+    float* tc_scal = nullptr;      // [4][4] device operand scales {2^k, 2^-k, scratch, -}
     float* x = nullptr;            // [L*L][128] residual stream fp32 (NHWC)
     __half* xh = nullptr;          // [L*L][128] fp16 high part of x
     __half* xl = nullptr;          // [L*L][128] fp16 low part
@@ -210,6 +218,7 @@ struct dmp2_engine {
     bool eig_no_cl16 = false;        // set when a 16-CTA cluster launch was refused
     bool attr_eig = false, attr_refine = false, attr_eig_grid = false;   // per-engine (= per-device) cudaFuncSetAttribute done
     StripCtx sp;                     // halo-sharded mode: window + peers (strip.cu)
+    bool gemm_tc = true;             // stem GEMM on the tcgen05 pipeline (DMP2_GEMM=ffma: CUDA-core validation path)
     bool fuse_stats = true;          // InstanceNorm sums come out of the conv epilogue (DMP2_FUSE_STATS=0: separate k_in_stats pass)
     bool strip_on = false;           // true while dmp2_fold_strip runs: the 2-D track works on rows [sp.r0, sp.r1)
     bool profile = false;            // record a CUDA-event pair around every conv launch (bench.py roofline)
@@ -253,7 +262,20 @@ int run_conv_tc(dmp2_engine* e, int blk, const __half* xh, const __half* xl, con
                 int H, int y_off, int map_rows, float* raw, int mode, cudaStream_t st, bool fuse_stats = false);
 bool conv_tc_fuses_stats(const dmp2_engine* e);      // true: run_conv_tc(..., fuse_stats = true) leaves ws.norm_ss / sp.totals ready
 int run_gemm_tn_test(dmp2_engine* e, const float* a, const float* b, int M, int N, int K, int mode, int chunk_k, float* c, cudaStream_t st);
-void conv_tc_invalidate(dmp2_engine* e);             // forget cached activation tensor maps (their buffers are being freed)
+void conv_tc_invalidate(dmp2_engine* e);
+// fp32 GEMMs on the tensor-core pipeline: scaled fp16 hi/lo split of an operand, and C = alpha * A B^T from split operands
+struct GemmTcEpilogue {               // epilogue variants of the MSA-feature GEMMs (see TcParams in conv_tc.cu)
+    int kind;                         // 0 plain, 1 Gram, 2 Woodbury, 3 covariance
+    int m_off;
+    const float* dsa;                 // device {scale, 1/scale} of the A / B operand split (nullptr = 1)
+    const float* dsb;
+    const float* scal;                // device scalars of predict.py:45-51: [1] = n_eff, [2] = ridge
+};
+int run_operand_scale(dmp2_engine* e, const float* x, int rows, int cols, int64_t ld, float* ds /* 3 floats */, cudaStream_t st);
+int run_split_scaled(dmp2_engine* e, const float* x, int rows, int cols, int64_t ld, float scale, const float* dscale, __half* hi,
+                     __half* lo, int Kp, cudaStream_t st);
+int run_gemm_tc(dmp2_engine* e, const __half* a_hi, const __half* a_lo, const __half* b_hi, const __half* b_lo, int M, int N, int Kp,
+                float alpha, float* c, int ldc, int chunk_k, cudaStream_t st, const GemmTcEpilogue* ep = nullptr, int b_rows = 0);             // forget cached activation tensor maps (their buffers are being freed)
 void conv_tc_destroy(dmp2_engine* e);
 // eig.cu
 int run_eig_top8(dmp2_engine* e, const float* m, int L, float* vals, float* mds_scaled, float* vecs_raw, cudaStream_t st);

@@ -78,6 +78,15 @@ struct TcParams {
     int num_kb;          // k-blocks per unit: conv 50, gemm K/64
     int chunk_kb;        // k-blocks per tcgen05 accumulation chain (conv: 2 = one tap)
     int M, N;            // gemm: rows, columns of C
+    int ldc;             // gemm: row stride of C (floats)
+    float alpha;         // gemm: C = alpha * A B^T
+    // gemm epilogue variants of the MSA-feature GEMMs (msa.cu): the operand scales live on the device (dsa/dsb point to
+    // {scale, 1/scale}; nullptr = 1) and so do the scalars of predict.py:45-51 (scal[1] = n_eff, scal[2] = ridge)
+    int ep;              // 0: alpha*acc   1 (Gram): acc + [m==n] ridge n_eff   2 (Woodbury): ([m==n] - acc) / ridge   3 (cov): acc / n_eff + [m==n] ridge
+    int m_off;           // row index of C's first row in the full matrix (diagonal test; halo-sharded Woodbury)
+    const float* dsa;
+    const float* dsb;
+    const float* scal;
     int n_tiles_n;       // column tiles of 256 (conv: 2)
     int units;           // cluster-level work units: ceil(row tiles / CL) * n_tiles_n
     float* out;          // conv: raw [pixels][128]; gemm: C [M][N]
@@ -133,14 +142,14 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // Sum v[i] over the 32 lanes of the warp; lane l ends up with the total of v[l] in v[0] (31 shuffles).
-__device__ __forceinline__ float lane_transpose_sum(float (&v)[32], int lane) {
+__device__ __forceinline__ double lane_transpose_sum(double (&v)[32], int lane) {
 #pragma unroll
     for (int s = 16; s >= 1; s >>= 1) {
         const bool up = (lane & s) != 0;
 #pragma unroll
         for (int i = 0; i < s; i++) {
-            const float send = up ? v[i] : v[i + s];
-            const float keep = up ? v[i + s] : v[i];
+            const double send = up ? v[i] : v[i + s];
+            const double keep = up ? v[i + s] : v[i];
             v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
         }
     }
@@ -394,11 +403,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv5_tc(const __grid_consta
             if (p.gemm) {
                 const int64_t row = u.m0 + r;
                 if (row < p.M) {
-                    float* dst = p.out + row * p.N + u.n0 + hcol * 128;
+                    float* dst = p.out + row * p.ldc + u.n0 + hcol * 128;
                     const int ncol = p.N - (u.n0 + hcol * 128);
+                    float al = p.alpha;
+                    if (p.dsa) al *= __ldg(p.dsa + 1);
+                    if (p.dsb) al *= __ldg(p.dsb + 1);
+                    float mul = al, dg = 0.f;                      // C = mul * acc + [m == n] * dg
+                    if (p.ep == 1) dg = __ldg(p.scal + 2) * __ldg(p.scal + 1);
+                    else if (p.ep == 2) { const float rr = 1.0f / __ldg(p.scal + 2); mul = -al * rr; dg = rr; }
+                    else if (p.ep == 3) { mul = al / __ldg(p.scal + 1); dg = __ldg(p.scal + 2); }
+                    const int dcol = (int)(row + p.m_off) - (u.n0 + hcol * 128);      // column of this thread's slice on the diagonal
 #pragma unroll
                     for (int i = 0; i < 32; i++)
-                        if (4 * i < ncol) *reinterpret_cast<float4*>(dst + 4 * i) = make_float4(R[4 * i], R[4 * i + 1], R[4 * i + 2], R[4 * i + 3]);
+                        if (4 * i < ncol) {
+                            float4 o = make_float4(mul * R[4 * i], mul * R[4 * i + 1], mul * R[4 * i + 2], mul * R[4 * i + 3]);
+                            if (p.ep != 0 && (dcol >> 2) == i) {
+                                if ((dcol & 3) == 0) o.x += dg; else if ((dcol & 3) == 1) o.y += dg; else if ((dcol & 3) == 2) o.z += dg; else o.w += dg;
+                            }
+                            *reinterpret_cast<float4*>(dst + 4 * i) = o;
+                        }
                 }
             } else {
                 const int y = u.y0 + (r >> 4), x = u.x0 + (r & 15);
@@ -415,14 +438,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv5_tc(const __grid_consta
 #pragma unroll
                     for (int i = 0; i < 8; i++) dst[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
                 }
-                if (p.stat_part) {                   // InstanceNorm partial sums: fp32 over the warp's 32 pixels, fp64 beyond
-                    float sq[32];
+                if (p.stat_part) {                   // InstanceNorm partial sums, fp64 throughout (the same sums k_in_stats forms)
+                    double sv[32];
 #pragma unroll
-                    for (int i = 0; i < 32; i++) { o[i] = valid ? o[i] : 0.f; sq[i] = o[i] * o[i]; }
-                    const float s1 = lane_transpose_sum(o, lane);
-                    const float s2 = lane_transpose_sum(sq, lane);
-                    if (u.nt & 1) { st_s[1] += (double)s1; st_q[1] += (double)s2; }
-                    else { st_s[0] += (double)s1; st_q[0] += (double)s2; }
+                    for (int i = 0; i < 32; i++) sv[i] = valid ? (double)o[i] : 0.0;
+                    const double s1 = lane_transpose_sum(sv, lane);
+#pragma unroll
+                    for (int i = 0; i < 32; i++) sv[i] = valid ? (double)o[i] * (double)o[i] : 0.0;
+                    const double s2 = lane_transpose_sum(sv, lane);
+                    if (u.nt & 1) { st_s[1] += s1; st_q[1] += s2; }
+                    else { st_s[0] += s1; st_q[0] += s2; }
                 }
             }
         }
@@ -615,7 +640,8 @@ int run_conv_tc(dmp2_engine* e, int blk, const __half* xh, const __half* xl, con
     maps.b_hi = s->wmap[blk][0]; maps.b_lo = s->wmap[blk][1]; maps.b8_w = s->wmap[blk][2]; maps.b8_lo = s->wmap[blk][3];
     TcParams p;
     p.gemm = 0; p.L = L; p.H = H; p.y_off = y_off; p.tiles_x = cdiv(L, TILE_W); p.num_kb = 50; p.chunk_kb = 2 * e->conv_chunk_taps;
-    p.M = H * L; p.N = 512; p.n_tiles_n = 2; p.out = raw; p.bias = bw.bias;
+    p.M = H * L; p.N = 512; p.ldc = 512; p.alpha = 1.0f; p.ep = 0; p.m_off = 0; p.dsa = nullptr; p.dsb = nullptr; p.scal = nullptr;
+    p.n_tiles_n = 2; p.out = raw; p.bias = bw.bias;
     p.stat_part = nullptr; p.ticket = nullptr; p.norm = nullptr; p.gamma = nullptr; p.totals = nullptr; p.npix = 0;
     if (fuse_stats) {
         p.stat_part = e->ws.stat_part; p.ticket = e->ws.ticket; p.norm = e->ws.norm_ss; p.gamma = bw.gamma;
@@ -663,13 +689,106 @@ int run_gemm_tn_test(dmp2_engine* e, const float* a, const float* b, int M, int 
         maps.a8_lo = maps.a_hi; maps.a8_hi = maps.a_hi; maps.b8_w = maps.b_hi; maps.b8_lo = maps.b_hi;    // unused in these modes
         TcParams p;
         p.gemm = 1; p.L = 0; p.H = 0; p.y_off = 0; p.tiles_x = 1; p.num_kb = K / KCHUNK; p.chunk_kb = chunk_k / KCHUNK;
-        p.M = M; p.N = N; p.n_tiles_n = cdiv(N, TILE_N); p.out = c; p.bias = nullptr;
+        p.M = M; p.N = N; p.ldc = N; p.alpha = 1.0f; p.ep = 0; p.m_off = 0; p.dsa = nullptr; p.dsb = nullptr; p.scal = nullptr;
+        p.n_tiles_n = cdiv(N, TILE_N); p.out = c; p.bias = nullptr;
         p.stat_part = nullptr; p.ticket = nullptr; p.norm = nullptr; p.gamma = nullptr; p.totals = nullptr; p.npix = 0;
         rc = launch_mode(e, mode, e->conv_cluster, maps, p, cdiv(M, TILE_M), st);
     } while (0);
     cudaStreamSynchronize(st);
     cudaFree(ah); cudaFree(al); cudaFree(bh); cudaFree(bl);
     return rc;
+}
+
+// ---- fp32 GEMMs of the other stages on the same tensor-core pipeline ---------------------------------------------
+// x (rows x cols, row stride ld) * scale -> fp16 hi / lo copies [rows][Kp], zero-padded to Kp columns.  `scale` is a
+// power of two chosen by the caller so that the values sit well inside the fp16 range (the lo parts are 2^-12 of the
+// values; without it small entries would lose their lo part to fp16 underflow).
+__global__ void __launch_bounds__(256) k_split_scaled(const float* __restrict__ x, int rows, int cols, int64_t ld, float scale,
+                                                      const float* __restrict__ dscale, __half* __restrict__ hi,
+                                                      __half* __restrict__ lo, int Kp) {
+    if (dscale) scale *= __ldg(dscale);
+    const int64_t n = (int64_t)rows * (Kp / 4);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / (Kp / 4)), c = (int)(i % (Kp / 4)) * 4;
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) v[j] = (c + j < cols) ? x[(int64_t)r * ld + c + j] * scale : 0.f;
+        __half2 h01 = __floats2half2_rn(v[0], v[1]), h23 = __floats2half2_rn(v[2], v[3]);
+        float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        __half2 l01 = __floats2half2_rn(v[0] - f01.x, v[1] - f01.y), l23 = __floats2half2_rn(v[2] - f23.x, v[3] - f23.y);
+        uint2 hv, lv;
+        hv.x = *reinterpret_cast<uint32_t*>(&h01); hv.y = *reinterpret_cast<uint32_t*>(&h23);
+        lv.x = *reinterpret_cast<uint32_t*>(&l01); lv.y = *reinterpret_cast<uint32_t*>(&l23);
+        *reinterpret_cast<uint2*>(hi + (int64_t)r * Kp + c) = hv;
+        *reinterpret_cast<uint2*>(lo + (int64_t)r * Kp + c) = lv;
+    }
+}
+
+// largest |x| of a rows x cols matrix -> ds = {2^k, 2^-k} with max * 2^k in [2^12, 2^13): the operand then sits in the
+// middle of the fp16 range and its lo part (2^-12 of it) stays normal
+__global__ void __launch_bounds__(256) k_absmax(const float* __restrict__ x, int rows, int cols, int64_t ld, unsigned int* __restrict__ mx) {
+    float m = 0.f;
+    const int64_t n = (int64_t)rows * cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        m = fmaxf(m, fabsf(x[(i / cols) * ld + (i % cols)]));
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(mx, __float_as_uint(m));             // non-negative floats order like their bit patterns
+}
+__global__ void k_scale_from_max(unsigned int* mx, float* ds) {
+    const float m = __uint_as_float(*mx);
+    int ex = 0;
+    if (m > 0.f && isfinite(m)) frexpf(m, &ex);                                   // m = f * 2^ex, f in [0.5, 1)
+    const int k = 13 - ex;                                                         // m * 2^k in [2^12, 2^13)
+    ds[0] = ldexpf(1.0f, k);
+    ds[1] = ldexpf(1.0f, -k);
+    *mx = 0u;
+}
+
+int run_operand_scale(dmp2_engine* e, const float* x, int rows, int cols, int64_t ld, float* ds, cudaStream_t st) {
+    unsigned int* mx = reinterpret_cast<unsigned int*>(ds + 2);                  // scratch word next to the pair, zero between uses
+    const int64_t n = (int64_t)rows * cols;
+    const int grid = (int)std::min<int64_t>(cdiv64(n, 1024), (int64_t)e->num_sms * 4);
+    k_absmax<<<std::max(grid, 1), 256, 0, st>>>(x, rows, cols, ld, mx);
+    POST_LAUNCH(e, "k_absmax");
+    k_scale_from_max<<<1, 1, 0, st>>>(mx, ds);
+    POST_LAUNCH(e, "k_scale_from_max");
+    return 0;
+}
+
+int run_split_scaled(dmp2_engine* e, const float* x, int rows, int cols, int64_t ld, float scale, const float* dscale, __half* hi,
+                     __half* lo, int Kp, cudaStream_t st) {
+    const int64_t n = (int64_t)rows * (Kp / 4);
+    const int grid = (int)std::min<int64_t>(cdiv64(n, 256), (int64_t)e->num_sms * 8);
+    k_split_scaled<<<grid, 256, 0, st>>>(x, rows, cols, ld, scale, dscale, hi, lo, Kp);
+    POST_LAUNCH(e, "k_split_scaled");
+    return 0;
+}
+
+// C[M][ldc] = alpha * A[M][Kp] * B[N][Kp]^T, operands given as fp16 hi/lo pairs (Kp % 64 == 0), 3 MMAs per MAC,
+// accumulation chains of chunk_k elements summed in fp32 registers.  Asynchronous on st, no allocation.
+int run_gemm_tc(dmp2_engine* e, const __half* a_hi, const __half* a_lo, const __half* b_hi, const __half* b_lo, int M, int N, int Kp,
+                float alpha, float* c, int ldc, int chunk_k, cudaStream_t st, const GemmTcEpilogue* ep, int b_rows) {
+    if (b_rows <= 0) b_rows = N;                                       // rows of B that exist (beyond them the TMA zero-fills)
+    if (M < 1 || N < 4 || N % 4 != 0 || Kp % KCHUNK != 0 || ldc % 4 != 0) return e->fail(DMP2_ERR_BAD_ARG, "gemm_tc: bad shape");
+    int ck = chunk_k > 0 ? chunk_k : 128;
+    while (ck > KCHUNK && Kp % ck != 0) ck -= KCHUNK;               // longest chain <= chunk_k that divides Kp
+    TcState* s;
+    TRY(get_state(e, &s));
+    ConvMaps maps;
+    uint64_t dims[3] = {(uint64_t)Kp, (uint64_t)M, 1};
+    uint64_t str[2] = {(uint64_t)Kp * 2, (uint64_t)Kp * 2 * (uint64_t)M};
+    uint32_t box[3] = {KCHUNK, TILE_M, 1};
+    TRY(encode(e, &maps.a_hi, a_hi, 2, 3, dims, str, box));
+    TRY(encode(e, &maps.a_lo, a_lo, 2, 3, dims, str, box));
+    TRY(weight_map(e, &maps.b_hi, b_hi, b_rows, Kp, 2));
+    TRY(weight_map(e, &maps.b_lo, b_lo, b_rows, Kp, 2));
+    maps.a8_lo = maps.a_hi; maps.a8_hi = maps.a_hi; maps.b8_w = maps.b_hi; maps.b8_lo = maps.b_hi;        // unused
+    TcParams p;
+    p.gemm = 1; p.L = 0; p.H = 0; p.y_off = 0; p.tiles_x = 1; p.num_kb = Kp / KCHUNK; p.chunk_kb = ck / KCHUNK;
+    p.M = M; p.N = N; p.ldc = ldc; p.alpha = alpha; p.n_tiles_n = cdiv(N, TILE_N); p.out = c; p.bias = nullptr;
+    p.ep = ep ? ep->kind : 0; p.m_off = ep ? ep->m_off : 0; p.dsa = ep ? ep->dsa : nullptr; p.dsb = ep ? ep->dsb : nullptr; p.scal = ep ? ep->scal : nullptr;
+    p.stat_part = nullptr; p.ticket = nullptr; p.norm = nullptr; p.gamma = nullptr; p.totals = nullptr; p.npix = 0;
+    return launch_mode(e, DMP2_CONV_TC_F16X3, e->conv_cluster, maps, p, cdiv(M, TILE_M), st);
 }
 
 void conv_tc_destroy(dmp2_engine* e) {

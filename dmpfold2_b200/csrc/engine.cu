@@ -147,6 +147,15 @@ static int load_weights(dmp2_engine* e, HostSD& sd) {
             wd[o] = lw[(size_t)o * 955 + 954];
         }
         TRY(upload(e, sw, &w.stem_w)); TRY(upload(e, wd, &w.stem_wd));
+        std::vector<__half> swh((size_t)384 * DMP2_STEM_KP, __float2half_rn(0.f)), swl(swh);
+        for (int o = 0; o < 384; o++)
+            for (int k = 0; k < DMP2_STEM_K; k++) {
+                const float v = sw[(size_t)o * DMP2_STEM_K + k] * DMP2_STEM_SW;
+                const __half h = __float2half_rn(v);
+                swh[(size_t)o * DMP2_STEM_KP + k] = h;
+                swl[(size_t)o * DMP2_STEM_KP + k] = __float2half_rn(v - __half2float(h));
+            }
+        TRY(upload(e, swh, &w.stem_w_hi)); TRY(upload(e, swl, &w.stem_w_lo));
         TRY(upload_raw(e, lb, 384, &w.stem_b)); TRY(upload_raw(e, g, 128, &w.stem_gamma)); TRY(upload_raw(e, b, 128, &w.stem_beta));
     }
     // ---- ResNet blocks
@@ -257,6 +266,12 @@ int ensure_workspace(dmp2_engine* e, int L, int N, int rows2d) {
     TRY(wsalloc(e, &ws.kmat, Npad64 * Npad64));
     TRY(wsalloc(e, &ws.wy, Npad * n4));
     TRY(wsalloc(e, &ws.gj_r, 64 * std::max(npad, Npad64)));
+    {   // fp16 hi/lo operands of the MSA-feature GEMMs: xc, wy^T [n][Kp2], K^-1 [Npad64][Kp2], xct [Npad][Kp1] (msa.cu)
+        const int64_t Kp2 = (Npad + 127) & ~(int64_t)127, Kp1 = (n4 + 127) & ~(int64_t)127;
+        TRY(wsalloc(e, &ws.dca_tc, 2 * (2 * n * Kp2 + Npad64 * Kp2 + Npad * Kp1)));
+        TRY(wsalloc(e, &ws.tc_scal, 16));
+        CUDA_TRY(e, cudaMemset(ws.tc_scal, 0, 16 * sizeof(float)));
+    }
     TRY(wsalloc(e, &ws.x3, P));
     TRY(wsalloc(e, &ws.apc, 2 * L + 1));
     TRY(wsalloc(e, &ws.feat, P * DMP2_FEAT_LD));
@@ -271,6 +286,7 @@ int ensure_workspace(dmp2_engine* e, int L, int N, int rows2d) {
     TRY(wsalloc(e, &ws.dmap, P));
     TRY(wsalloc(e, &ws.base384, P2 * 384));
     TRY(wsalloc(e, &ws.raw, P2 * 128));
+    TRY(wsalloc(e, &ws.tc_scratch, (int64_t)4 * DMP2_TC_SLAB * 1024));
     TRY(wsalloc(e, &ws.x, P2 * 128));
     TRY(wsalloc(e, &ws.xh, PA * 128));
     TRY(wsalloc(e, &ws.xl, PA * 128));
@@ -433,6 +449,8 @@ int dmp2_create(dmp2_engine** out, int device, int n_tensors, const char* const*
     const char* cs = getenv("DMP2_CONV_SMS");
     if (cs && atoi(cs) > 0) e->conv_sms = atoi(cs);
     const char* vm = getenv("DMP2_VGRU");
+    const char* gm = getenv("DMP2_GEMM");
+    if (gm && !strcmp(gm, "ffma")) e->gemm_tc = false;
     const char* fs = getenv("DMP2_FUSE_STATS");
     if (fs) e->fuse_stats = strcmp(fs, "0") != 0;
     if (vm && !strcmp(vm, "ffma")) e->vgru_mode = 1;

@@ -370,7 +370,50 @@ int run_dca(dmp2_engine* e, const uint8_t* msa, int N, int L, const float* w, fl
     if (woodbury && n4 != n) CUDA_TRY(e, cudaMemsetAsync(ws.xct, 0, (size_t)Npad * n4 * sizeof(float), st));   // pad columns
     k_center<<<dim3(cdiv(Npad, 256), L), 256, 0, st>>>(ws.msa_t, w, mean, N, Npad, ws.xc, woodbury ? ws.xct : nullptr, n4);
     POST_LAUNCH(e, "k_center");
-    if (!woodbury) {
+    // ---- tensor-core form of the dense contractions (default; DMP2_GEMM=ffma keeps them on the CUDA-core GEMM) -------
+    // Every fp32 operand is split into an fp16 hi/lo pair after a power-of-two scaling that centres it in the fp16 range
+    // (scale found on the device: run_operand_scale); products are exact, 3 MMAs per MAC, accumulation chains of 128
+    // summed in fp32 registers (conv_tc.cu) -- at least as accurate as the sequential fp32 sums of the CUDA-core path.
+    const int Kp2 = (Npad + 127) & ~127;                   // contraction over the sequence axis
+    const int Kp1 = (n4 + 127) & ~127;                     // contraction over the 21 L axis (Gram matrix)
+    __half* t = ws.dca_tc;
+    __half *x_hi = t, *x_lo = x_hi + (int64_t)n * Kp2;                                            // xc   [n][Kp2]
+    __half *w_hi = x_lo + (int64_t)n * Kp2, *w_lo = w_hi + (int64_t)n * Kp2;                      // wy^T [n][Kp2]
+    __half *k_hi = w_lo + (int64_t)n * Kp2, *k_lo = k_hi + (int64_t)Npad64 * Kp2;                 // K^-1 [Npad64][Kp2]
+    __half *xt_hi = k_lo + (int64_t)Npad64 * Kp2, *xt_lo = xt_hi + (int64_t)Npad * Kp1;           // xct  [Npad][Kp1]
+    float *ds_x = ws.tc_scal, *ds_k = ws.tc_scal + 4, *ds_w = ws.tc_scal + 8;
+    if (e->gemm_tc) {
+        TRY(run_operand_scale(e, ws.xc, n, Npad, Npad, ds_x, st));
+        TRY(run_split_scaled(e, ws.xc, n, Npad, Npad, 1.0f, ds_x, x_hi, x_lo, Kp2, st));
+    }
+    if (!woodbury && e->gemm_tc) {
+        const GemmTcEpilogue ep{3, 0, ds_x, ds_x, ws.scal};
+        TRY(run_gemm_tc(e, x_hi, x_lo, x_hi, x_lo, n, n4, Kp2, 1.0f, ws.cov, npad, 128, st, &ep, n));      // covariance (predict.py:50-51)
+        if (npad != n) {
+            k_pad_identity<<<(unsigned)cdiv64((int64_t)npad * npad, 256), 256, 0, st>>>(ws.cov, n, npad);
+            POST_LAUNCH(e, "k_pad_identity");
+        }
+        TRY(gj_invert(e, ws.cov, npad, st));
+    } else if (woodbury && e->gemm_tc) {
+        TRY(run_split_scaled(e, ws.xct, Npad, n4, n4, 1.0f, ds_x, xt_hi, xt_lo, Kp1, st));
+        const GemmTcEpilogue epg{1, 0, ds_x, ds_x, ws.scal};
+        TRY(run_gemm_tc(e, xt_hi, xt_lo, xt_hi, xt_lo, Npad, Npad, Kp1, 1.0f, ws.kmat, Npad64, 128, st, &epg));   // Gram system
+        k_pad_identity<<<(unsigned)cdiv64((int64_t)Npad64 * Npad64, 256), 256, 0, st>>>(ws.kmat, N, Npad64);
+        POST_LAUNCH(e, "k_pad_identity");
+        TRY(gj_invert(e, ws.kmat, Npad64, st));
+        // wy^T = X K^-1 (K^-1 is symmetric, so its rows serve as the K-major B operand), then inv = (I - X wy) / ridge
+        TRY(run_operand_scale(e, ws.kmat, Npad, Npad, Npad64, ds_k, st));
+        TRY(run_split_scaled(e, ws.kmat, Npad, Npad, Npad64, 1.0f, ds_k, k_hi, k_lo, Kp2, st));
+        const GemmTcEpilogue epy{0, 0, ds_x, ds_k, ws.scal};
+        float* wyt = ws.wy;                                // [n][Npad] fp32
+        TRY(run_gemm_tc(e, x_hi, x_lo, k_hi, k_lo, n, Npad, Kp2, 1.0f, wyt, Npad, 128, st, &epy));
+        TRY(run_operand_scale(e, wyt, n, Npad, Npad, ds_w, st));
+        TRY(run_split_scaled(e, wyt, n, Npad, Npad, 1.0f, ds_w, w_hi, w_lo, Kp2, st));
+        const GemmTcEpilogue epw{2, 21 * rw.r0, ds_x, ds_w, ws.scal};
+        // halo-sharded: only the rows of the inverse that feed this rank's strip of the pair features
+        TRY(run_gemm_tc(e, x_hi + (int64_t)21 * rw.r0 * Kp2, x_lo + (int64_t)21 * rw.r0 * Kp2, w_hi, w_lo, 21 * rw.R, n4, Kp2, 1.0f,
+                        ws.cov + (int64_t)21 * rw.r0 * npad, npad, 128, st, &epw, n));
+    } else if (!woodbury) {
         sgemm_launch<8>(n, n, Npad, LoadRowMajorK{ws.xc, Npad}, LoadRowMajorK{ws.xc, Npad}, CovEpilogue{ws.cov, npad, ws.scal}, st);
         POST_LAUNCH(e, "sgemm<cov>");
         if (npad != n) {

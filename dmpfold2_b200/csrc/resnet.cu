@@ -35,23 +35,75 @@ struct StemLoad {
     }
 };
 
+// The A operand of the stem GEMM for `rows` pixels starting at pixel m0, as the fp16 hi/lo pair the tensor-core GEMM
+// reads: [rows][DMP2_STEM_KP], columns 0..511 = outer product, 512..955 = DCA features (+ APC, + 2 zero pads), rest 0.
+// Values are multiplied by STEM_SA (a power of two) so that the lo parts stay inside the fp16 range.
+constexpr float STEM_SA = 16.0f;
+__global__ void __launch_bounds__(256) k_stem_operand(const float* __restrict__ m1t, const float* __restrict__ feat, int L, int64_t m0,
+                                                      int rows, __half* __restrict__ hi, __half* __restrict__ lo) {
+    constexpr int KQ = DMP2_STEM_KP / 4;
+    const int64_t n = (int64_t)rows * KQ;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(idx / KQ), k = (int)(idx % KQ) * 4;
+        const int64_t pix = m0 + r;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < 512) {
+            const int i = (int)(pix / L), j = (int)(pix - (int64_t)i * L);
+            const float4 a = *reinterpret_cast<const float4*>(m1t + (int64_t)i * 512 + k);
+            const float4 b = *reinterpret_cast<const float4*>(m1t + (int64_t)j * 512 + k);
+            v = make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
+        } else if (k < 512 + DMP2_FEAT_LD) {
+            v = *reinterpret_cast<const float4*>(feat + pix * DMP2_FEAT_LD + (k - 512));
+        }
+        v.x *= STEM_SA; v.y *= STEM_SA; v.z *= STEM_SA; v.w *= STEM_SA;
+        __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+        float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        __half2 l01 = __floats2half2_rn(v.x - f01.x, v.y - f01.y), l23 = __floats2half2_rn(v.z - f23.x, v.w - f23.y);
+        uint2 hv, lv;
+        hv.x = *reinterpret_cast<uint32_t*>(&h01); hv.y = *reinterpret_cast<uint32_t*>(&h23);
+        lv.x = *reinterpret_cast<uint32_t*>(&l01); lv.y = *reinterpret_cast<uint32_t*>(&l23);
+        *reinterpret_cast<uint2*>(hi + (int64_t)r * DMP2_STEM_KP + k) = hv;
+        *reinterpret_cast<uint2*>(lo + (int64_t)r * DMP2_STEM_KP + k) = lv;
+    }
+}
+
+// base384 WITHOUT the bias when the tensor-core GEMM produced it (k_stem_update adds it), with it on the CUDA-core path
 int run_stem_base(dmp2_engine* e, const float* mat1d_t, const float* feat444, int L, cudaStream_t st) {
     const Rows rw = rows_of(e, L);
-    sgemm_launch<8>(rw.R * L, 384, DMP2_STEM_K, StemLoad{mat1d_t, feat444, L, rw.r0 * L}, LoadRowMajorK{e->w.stem_w, DMP2_STEM_K},
-                    StoreRowMajor{e->ws.base384, 384, e->w.stem_b, 1.0f}, st);
-    POST_LAUNCH(e, "sgemm<stem>");
+    if (!e->gemm_tc) {
+        sgemm_launch<8>(rw.R * L, 384, DMP2_STEM_K, StemLoad{mat1d_t, feat444, L, rw.r0 * L}, LoadRowMajorK{e->w.stem_w, DMP2_STEM_K},
+                        StoreRowMajor{e->ws.base384, 384, e->w.stem_b, 1.0f}, st);
+        POST_LAUNCH(e, "sgemm<stem>");
+        return 0;
+    }
+    // 66 GFLOP at L=300: the pixels go through the tcgen05 GEMM (fp16 hi/lo split, K=128 accumulation chains) in slabs
+    // that fit the operand scratch
+    const int64_t npix = (int64_t)rw.R * L, first = (int64_t)rw.r0 * L;
+    __half* a_hi = e->ws.tc_scratch;
+    __half* a_lo = a_hi + (int64_t)DMP2_TC_SLAB * DMP2_STEM_KP;
+    for (int64_t m0 = 0; m0 < npix; m0 += DMP2_TC_SLAB) {
+        const int rows = (int)std::min<int64_t>(DMP2_TC_SLAB, npix - m0);
+        const int grid = (int)std::min<int64_t>(cdiv64((int64_t)rows * (DMP2_STEM_KP / 4), 256), (int64_t)e->num_sms * 8);
+        k_stem_operand<<<grid, 256, 0, st>>>(mat1d_t, feat444, L, first + m0, rows, a_hi, a_lo);
+        POST_LAUNCH(e, "k_stem_operand");
+        TRY(run_gemm_tc(e, a_hi, a_lo, e->w.stem_w_hi, e->w.stem_w_lo, rows, 384, DMP2_STEM_KP, 1.0f / (STEM_SA * DMP2_STEM_SW),
+                        e->ws.base384 + m0 * 384, 384, 128, st));
+    }
     return 0;
 }
 
 // raw[p][g] = max_{q<3} (base[p][3g+q] + wd[3g+q] * dmap[p])                    (network.py:30-31, pool 3)
 __global__ void __launch_bounds__(256) k_stem_update(const float* __restrict__ base, const float* __restrict__ wd,
+                                                     const float* __restrict__ bias /* nullptr: already in base */,
                                                      const float* __restrict__ dmap, int64_t npix, float* __restrict__ raw) {
     int g = threadIdx.x & 127;
     float w0 = wd[3 * g], w1 = wd[3 * g + 1], w2 = wd[3 * g + 2];
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+    if (bias) { c0 = bias[3 * g]; c1 = bias[3 * g + 1]; c2 = bias[3 * g + 2]; }
     for (int64_t p = (int64_t)blockIdx.x * 2 + (threadIdx.x >> 7); p < npix; p += (int64_t)gridDim.x * 2) {
         float d = dmap[p];
         const float* b = base + p * 384 + 3 * g;
-        float v = fmaxf(fmaxf(fmaf(w0, d, b[0]), fmaf(w1, d, b[1])), fmaf(w2, d, b[2]));
+        float v = fmaxf(fmaxf(fmaf(w0, d, b[0] + c0), fmaf(w1, d, b[1] + c1)), fmaf(w2, d, b[2] + c2));
         raw[p * 128 + g] = v;
     }
 }
@@ -219,7 +271,7 @@ int run_stem_update(dmp2_engine* e, const float* dmap, int L, cudaStream_t st) {
     const Rows rw = rows_of(e, L);
     const int64_t npix = (int64_t)rw.R * L;
     int grid = (int)std::min<int64_t>(cdiv64(npix, 2), (int64_t)e->num_sms * 8);
-    k_stem_update<<<grid, 256, 0, st>>>(ws.base384, e->w.stem_wd, dmap + (int64_t)rw.r0 * L, npix, ws.raw);
+    k_stem_update<<<grid, 256, 0, st>>>(ws.base384, e->w.stem_wd, e->gemm_tc ? e->w.stem_b : nullptr, dmap + (int64_t)rw.r0 * L, npix, ws.raw);
     POST_LAUNCH(e, "k_stem_update");
     return run_norm_gate(e, -1, ws.raw, ws.x, L, true, st);
 }

@@ -73,8 +73,8 @@ __global__ void __launch_bounds__(VT_THREADS, 1) k_vgru_step(const __grid_consta
     const uint32_t bar_base = base + VT_STAGES * VT_STAGE_BYTES;
     auto full = [&](int s) { return bar_base + 8u * s; };
     auto empty = [&](int s) { return bar_base + 8u * (VT_STAGES + s); };
-    const uint32_t acc_full = bar_base + 8u * (2 * VT_STAGES);
-    const uint32_t tmem_slot = acc_full + 8;
+    auto acc_full = [&](int c) { return bar_base + 8u * (2 * VT_STAGES + c); };          // one per accumulation chain
+    const uint32_t tmem_slot = acc_full(VT_NACC);
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(VT_THREADS, 1) k_vgru_step(const __grid_consta
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < VT_STAGES; s++) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
-        mbar_init(acc_full, 1);
+        for (int c = 0; c < VT_NACC; c++) mbar_init(acc_full(c), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -144,9 +144,9 @@ __global__ void __launch_bounds__(VT_THREADS, 1) k_vgru_step(const __grid_consta
                     tc_mma_f16(d, make_smem_desc(a_hi + k * 32), make_smem_desc(b_lo + k * 32), idesc, 1u);
                 }
                 tc_commit(empty(s));
+                if (kb & 1) tc_commit(acc_full(kb >> 1));          // chain finished: the epilogue may read it while the next one runs
                 if (++s == VT_STAGES) { s = 0; ph ^= 1; }
             }
-            tc_commit(acc_full);
         }
     } else {
         // 16 epilogue warps: TMEM lane quarter q = warp % 4 (hardware rule), unit quarter uq = 0..3 -> 8 units per thread.
@@ -170,25 +170,21 @@ __global__ void __launch_bounds__(VT_THREADS, 1) k_vgru_step(const __grid_consta
 #pragma unroll
             for (int v = 0; v < 2; v++) *reinterpret_cast<float4*>(&ho[4 * v]) = *reinterpret_cast<const float4*>(hp + 4 * v);
         }
-        mbar_wait(acc_full, 0);
-        tc_fence_after();
         float ar[8], az[8], an[8];
 #pragma unroll
-        for (int c = 0; c < VT_NACC; c += 2) {                 // two chains per round trip: (c0 + c1) + (c2 + c3)
-            float pr[2][8], pz[2][8], pn[2][8];
-#pragma unroll
-            for (int u = 0; u < 2; u++) {
-                tmem_ld8(lane_addr + (c + u) * 128, pr[u]);
-                tmem_ld8(lane_addr + (c + u) * 128 + 32, pz[u]);
-                tmem_ld8(lane_addr + (c + u) * 128 + 64, pn[u]);
-            }
+        for (int c = 0; c < VT_NACC; c++) {                    // chains are read as they complete, behind the MMAs of the next ones
+            mbar_wait(acc_full(c), 0);
+            tc_fence_after();
+            float pr[8], pz[8], pn[8];
+            tmem_ld8(lane_addr + c * 128, pr);
+            tmem_ld8(lane_addr + c * 128 + 32, pz);
+            tmem_ld8(lane_addr + c * 128 + 64, pn);
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                const float sr = pr[0][j] + pr[1][j], sz = pz[0][j] + pz[1][j], sn = pn[0][j] + pn[1][j];
-                ar[j] = c == 0 ? sr : ar[j] + sr;
-                az[j] = c == 0 ? sz : az[j] + sz;
-                an[j] = c == 0 ? sn : an[j] + sn;
+                ar[j] = c == 0 ? pr[j] : ar[j] + pr[j];
+                az[j] = c == 0 ? pz[j] : az[j] + pz[j];
+                an[j] = c == 0 ? pn[j] : an[j] + pn[j];
             }
         }
         if (valid) {

@@ -59,6 +59,33 @@ def test_dca_features(eng, pf10963):
     assert float(eng.dca(msa[:1]).abs().max()) == 0.0
 
 
+def test_gemm_paths_tensor_core_vs_cuda_core(state_dict, oracle, pf10963, monkeypatch):
+    """The dense contractions of the MSA features (Gram / covariance / Woodbury products) and the stem GEMM run on the
+    tcgen05 pipeline by default; DMP2_GEMM=ffma keeps them on the CUDA-core fp32 GEMM.  Both must agree with the oracle
+    (Woodbury branch, direct-covariance branch, ragged sizes) and with each other."""
+    from dmpfold2_b200.engine import Engine
+    cases = [pf10963, _rand_msa(53, 23, 11), O.synth_msa_structured(pf10963, 30, 700, 5)]       # last: N >= 21 L (direct branch)
+    outs = {}
+    for mode in ('tc', 'ffma'):
+        if mode == 'ffma':
+            monkeypatch.setenv('DMP2_GEMM', 'ffma')
+        e = Engine(state_dict, 0)
+        try:
+            outs[mode] = [e.dca(m).cpu() for m in cases]
+            m1 = torch.tanh(torch.randn(33, 512, generator=torch.Generator().manual_seed(3)))
+            outs[mode].append(e.resnet_pass(m1, outs[mode][1].new_zeros(33, 33, 442).normal_(generator=torch.Generator().manual_seed(4)),
+                                            torch.full((33, 33), -1.0)).cpu())
+        finally:
+            e.close()
+    for i, m in enumerate(cases):
+        ref = O.msa_features(torch.from_numpy(m))
+        scale = max(1.0, float(ref.abs().max()))
+        for mode in ('tc', 'ffma'):
+            assert (outs[mode][i] - ref).abs().max() < 3e-4 * scale, (mode, i, float((outs[mode][i] - ref).abs().max()))
+        assert (outs['tc'][i] - outs['ffma'][i]).abs().max() < 1e-4 * scale
+    assert _rel(outs['tc'][3], outs['ffma'][3]) < 1e-4
+
+
 def test_vgru(eng, oracle, pf10963):
     for msa in (pf10963[:60, :41], _rand_msa(9, 70, 4)):
         ref = oracle.vgru_last(torch.from_numpy(msa))
