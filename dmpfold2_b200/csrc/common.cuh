@@ -213,7 +213,9 @@ struct dmp2_engine {
     void* vt_state = nullptr;        // tensor-core vgru state, owned by vgru_tc.cu
     int conv_cluster = 0;            // conv kernel form: 0 = cta_group::2 CTA pairs, 1 = independent CTAs, 2 = 2-CTA weight multicast (DMP2_CONV_CLUSTER=pair|1|2)
     int conv_sms = 0;                // SMs the persistent conv kernel occupies (0 = all)
-    int conv_chunk_taps = 1;         // taps per tcgen05 accumulation chain (1, 5 or 25; DMP2_CONV_CHUNK): longer chains = fewer TMEM drains, larger truncation error
+    int conv_chunk_taps = 0;         // taps per tcgen05 accumulation chain (1, 5 or 25; DMP2_CONV_CHUNK); 0 = per mode: 1 for f16x3 (whose
+                                     // operands are exact to 2^-22, so the chain length IS its error), 5 for f16f8 / f16 (operand error 6e-6 / 1e-4
+                                     // dwarfs the 6e-7 of a 5-tap chain; 2-3 % faster)
     int vgru_mode = 0;               // 0 = tensor cores, one launch per MSA row; 1 = CUDA-core fp32 validation path
     bool eig_no_cl16 = false;        // set when a 16-CTA cluster launch was refused
     bool attr_eig = false, attr_refine = false, attr_eig_grid = false;   // per-engine (= per-device) cudaFuncSetAttribute done

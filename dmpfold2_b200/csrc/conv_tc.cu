@@ -639,7 +639,8 @@ int run_conv_tc(dmp2_engine* e, int blk, const __half* xh, const __half* xl, con
     maps.a_hi = s->amap[0]; maps.a_lo = s->amap[1]; maps.a8_lo = s->amap[2]; maps.a8_hi = s->amap[3];
     maps.b_hi = s->wmap[blk][0]; maps.b_lo = s->wmap[blk][1]; maps.b8_w = s->wmap[blk][2]; maps.b8_lo = s->wmap[blk][3];
     TcParams p;
-    p.gemm = 0; p.L = L; p.H = H; p.y_off = y_off; p.tiles_x = cdiv(L, TILE_W); p.num_kb = 50; p.chunk_kb = 2 * e->conv_chunk_taps;
+    p.gemm = 0; p.L = L; p.H = H; p.y_off = y_off; p.tiles_x = cdiv(L, TILE_W); p.num_kb = 50;
+    p.chunk_kb = 2 * (e->conv_chunk_taps > 0 ? e->conv_chunk_taps : (mode == DMP2_CONV_TC_F16X3 ? 1 : 5));
     p.M = H * L; p.N = 512; p.ldc = 512; p.alpha = 1.0f; p.ep = 0; p.m_off = 0; p.dsa = nullptr; p.dsb = nullptr; p.scal = nullptr;
     p.n_tiles_n = 2; p.out = raw; p.bias = bw.bias;
     p.stat_part = nullptr; p.ticket = nullptr; p.norm = nullptr; p.gamma = nullptr; p.totals = nullptr; p.npix = 0;

@@ -530,6 +530,13 @@ int dmp2_conv_profile(dmp2_engine* e, int* n_launches, float* total_ms) {
     return 0;
 }
 
+int dmp2_reserve(dmp2_engine* e, int L, int N) {
+    if (!e) return DMP2_ERR_BAD_ARG;
+    if (L < 8 || N < 1) return e->fail(DMP2_ERR_BAD_ARG, "reserve: need L >= 8 and N >= 1");
+    TRY(check_device(e));
+    return ensure_workspace(e, L, N);
+}
+
 int dmp2_fold(dmp2_engine* e, const uint8_t* msa_dev, int N, int L, const float* tmpl_ca_dev, int iterations, int minsteps,
               float* coords_out_dev, float* conf_out_dev, void* stream) {
     if (!e) return DMP2_ERR_BAD_ARG;

@@ -32,6 +32,7 @@ _SIGS = {
     'dmp2_debug_eig_phases': (_i, [_vp, _i, C.POINTER(C.c_double), _i]),
     'dmp2_set_profile': (_i, [_vp, _i]),
     'dmp2_conv_profile': (_i, [_vp, C.POINTER(_i), C.POINTER(C.c_float)]),
+    'dmp2_reserve': (_i, [_vp, _i, _i]),
     'dmp2_fold': (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp]),
     'dmp2_fold_host': (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _vp]),
     'dmp2_strip_rows': (_i, [_i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
@@ -163,6 +164,12 @@ class Engine:
 
     def set_profile(self, on: bool):
         self._check(self.lib.dmp2_set_profile(self.h, 1 if on else 0), 'dmp2_set_profile')
+
+    def reserve(self, l: int, n: int):
+        """Size the workspace for alignments up to (n rows, l columns): later folds within those bounds allocate nothing
+        (a fold that outgrows the workspace re-allocates, which synchronises the device once)."""
+        with torch.cuda.device(self.device):
+            self._check(self.lib.dmp2_reserve(self.h, int(l), int(n)), 'dmp2_reserve')
 
     def conv_profile(self) -> Tuple[int, float]:
         """(number of conv launches, their summed device time in ms) since the last call."""

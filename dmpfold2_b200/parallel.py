@@ -111,6 +111,10 @@ class StreamPool:
             for t, msa in enumerate(msas):
                 out[t] = self.engines[t % k].fold(msa, None if templates is None else templates[t], iterations, minsteps)
             return out
+        if len(msas) and hasattr(self.engines[0], 'reserve'):        # no allocation (= device sync) inside the folds
+            lmax, nmax = max(int(m.shape[1]) for m in msas), max(int(m.shape[0]) for m in msas)
+            for e in self.engines:
+                e.reserve(lmax, nmax)
         streams = self._cuda_streams()
         cur = torch.cuda.current_stream(torch.device('cuda', self.device_index))
         for s in streams:

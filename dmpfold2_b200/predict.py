@@ -175,6 +175,14 @@ def alns_to_coords(input_files, device='cuda', templates=None, iterations=defaul
     return fold_many(list(zip(input_files, templates)), one, gather=gather)
 
 
+def confidence_summary(confs, threshold: float = 0.5) -> Dict[str, float]:
+    """Convenience summary of the per-residue confidences aln_to_coords returns (the reference prints only their mean,
+    `REMARK  CONF:`, predict.py:196): mean, min, max and the fraction of residues at or above `threshold`."""
+    c = confs.detach().float().cpu().numpy() if torch.is_tensor(confs) else np.asarray(confs, dtype=np.float32)
+    return {'mean': float(c.mean()), 'min': float(c.min()), 'max': float(c.max()),
+            'fraction_confident': float((c >= threshold).mean()), 'threshold': float(threshold), 'residues': int(c.size)}
+
+
 _RNAMES = {0: 'ALA', 1: 'ARG', 2: 'ASN', 3: 'ASP', 4: 'CYS', 5: 'GLN', 6: 'GLU', 7: 'GLY', 8: 'HIS', 9: 'ILE', 10: 'LEU',
            11: 'LYS', 12: 'MET', 13: 'PHE', 14: 'PRO', 15: 'SER', 16: 'THR', 17: 'TRP', 18: 'TYR', 19: 'VAL'}
 

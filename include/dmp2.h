@@ -89,6 +89,11 @@ int dmp2_conv_profile(dmp2_engine* e, int* n_launches, float* total_ms);
 int dmp2_fold(dmp2_engine* e, const uint8_t* msa_dev, int N, int L, const float* tmpl_ca_dev, int iterations,
               int minsteps, float* coords_out_dev, float* conf_out_dev, void* stream);
 
+/* Size the engine's workspace for alignments of up to N rows x L columns now, so that later dmp2_fold calls within
+ * those bounds allocate nothing.  (A fold that needs a LARGER workspace than any seen before re-allocates, which
+ * synchronises the device once; reserve the maximum up front to keep dmp2_fold strictly asynchronous.) */
+int dmp2_reserve(dmp2_engine* e, int L, int N);
+
 /* Same with HOST buffers: copies the alignment up, runs the fold, copies coords/conf back and
  * synchronises.  This is the call timed as the end-to-end number. */
 int dmp2_fold_host(dmp2_engine* e, const uint8_t* msa_host, int N, int L, const float* tmpl_ca_host, int iterations,

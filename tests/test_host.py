@@ -113,6 +113,15 @@ def test_a3m_to_aln(tmp_path):
     assert P.encode_aln(P.read_aln(str(out))).shape == (3, 5)
 
 
+def test_confidence_summary_and_import_alias():
+    import numpy as np
+    import dmpfold
+    import dmpfold2_b200
+    assert dmpfold.aln_to_coords is dmpfold2_b200.aln_to_coords and dmpfold.run_dmpfold is dmpfold2_b200.run_dmpfold
+    s = dmpfold2_b200.confidence_summary(np.array([0.2, 0.6, 0.9, 0.5], dtype=np.float32))
+    assert s['residues'] == 4 and abs(s['mean'] - 0.55) < 1e-6 and s['fraction_confident'] == 0.75 and abs(s['min'] - 0.2) < 1e-6
+
+
 def test_product_never_touches_the_oracle():
     """The oracle is test infrastructure: nothing in the shipped package may import it, and bench.py may do so only
     inside its CPU-baseline leg."""
