@@ -17,6 +17,8 @@
 #define DMP2_STEM_K (512 + DMP2_FEAT_LD)
 #define DMP2_STEM_KP 1024     // K of the stem GEMM padded to whole 128-element accumulation chains (tensor-core path)
 #define DMP2_STEM_SW 256.0f   // power-of-two scale of the stem weights in their fp16 hi/lo copies
+#define DMP2_GRU_SW 1024.0f   // power-of-two scale of the GRU input weights in their fp16 hi/lo copies
+#define DMP2_GRU_SA 64.0f     // ... and of the GRU layer inputs (hidden states in [-1,1], MDS coordinates up to a few 10)
 #define DMP2_TC_SLAB 32768    // rows of a GEMM A operand staged at a time in ws.tc_scratch
 
 struct Launch {              // per-engine launch bookkeeping (gpu_launches) + sticky error
@@ -61,6 +63,8 @@ struct GruDir {              // one direction of one layer of a hidden-256 bidir
 struct BiGruLayer {
     float* w_ih;             // [1536][K] : rows 0..767 forward, 768..1535 reverse  (K = input width, mult of 4)
     float* b_ih;             // [1536]
+    __half* w_ih_hi;         // [1536][Kp] fp16 hi/lo split of w_ih * DMP2_GRU_SW (tensor-core input projection), Kp = K rounded up to 64
+    __half* w_ih_lo;
     int K;
     GruDir dir[2];
 };
@@ -272,6 +276,7 @@ struct GemmTcEpilogue {               // epilogue variants of the MSA-feature GE
     const float* dsa;                 // device {scale, 1/scale} of the A / B operand split (nullptr = 1)
     const float* dsb;
     const float* scal;                // device scalars of predict.py:45-51: [1] = n_eff, [2] = ridge
+    const float* bias = nullptr;      // kind 0 only: per-column bias [N] added after the scaling
 };
 int run_operand_scale(dmp2_engine* e, const float* x, int rows, int cols, int64_t ld, float* ds /* 3 floats */, cudaStream_t st);
 int run_split_scaled(dmp2_engine* e, const float* x, int rows, int cols, int64_t ld, float scale, const float* dscale, __half* hi,

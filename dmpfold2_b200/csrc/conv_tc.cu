@@ -417,6 +417,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv5_tc(const __grid_consta
                     for (int i = 0; i < 32; i++)
                         if (4 * i < ncol) {
                             float4 o = make_float4(mul * R[4 * i], mul * R[4 * i + 1], mul * R[4 * i + 2], mul * R[4 * i + 3]);
+                            if (p.bias) {                          // plain GEMM + per-column bias (GRU input projections)
+                                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + u.n0 + hcol * 128 + 4 * i));
+                                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                            }
                             if (p.ep != 0 && (dcol >> 2) == i) {
                                 if ((dcol & 3) == 0) o.x += dg; else if ((dcol & 3) == 1) o.y += dg; else if ((dcol & 3) == 2) o.z += dg; else o.w += dg;
                             }
@@ -788,6 +792,7 @@ int run_gemm_tc(dmp2_engine* e, const __half* a_hi, const __half* a_lo, const __
     p.gemm = 1; p.L = 0; p.H = 0; p.y_off = 0; p.tiles_x = 1; p.num_kb = Kp / KCHUNK; p.chunk_kb = ck / KCHUNK;
     p.M = M; p.N = N; p.ldc = ldc; p.alpha = alpha; p.n_tiles_n = cdiv(N, TILE_N); p.out = c; p.bias = nullptr;
     p.ep = ep ? ep->kind : 0; p.m_off = ep ? ep->m_off : 0; p.dsa = ep ? ep->dsa : nullptr; p.dsb = ep ? ep->dsb : nullptr; p.scal = ep ? ep->scal : nullptr;
+    p.bias = ep ? ep->bias : nullptr;
     p.stat_part = nullptr; p.ticket = nullptr; p.norm = nullptr; p.gamma = nullptr; p.totals = nullptr; p.npix = 0;
     return launch_mode(e, DMP2_CONV_TC_F16X3, e->conv_cluster, maps, p, cdiv(M, TILE_M), st);
 }

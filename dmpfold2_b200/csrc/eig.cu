@@ -78,6 +78,11 @@ __device__ __forceinline__ double block_sum1(double v, double* scr) {
 
 // rows_smem: doubles of shared memory reserved for the matrix rows (0 = rows stay in global memory A)
 // vec_smem:  1 = the inverse-iteration work vectors (32 n doubles) live in shared memory
+// inverse-iteration sweeps per eigenvector (DMP2_EIG_INVIT overrides; the shifts come out of the Sturm multi-section
+// accurate to ~1e-15 relative, so the second sweep already reproduces fp64 LAPACK eigenvectors to 1e-8: a third changes
+// nothing in max|dvec| (7.2e-9 at L=300, profiles/round2_eig.txt) and costs 73 us)
+__device__ int g_invit_iters = 2;
+
 template <int EIG_CL>
 __global__ void __launch_bounds__(EIG_THREADS, 1)
 k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* __restrict__ V, double* __restrict__ wk,
@@ -304,7 +309,8 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
     }
     __syncthreads();
     const double pivmin = fmax(tnorm * 2.3e-16, 1e-290);
-    for (int iter = 0; iter < 3; iter++) {
+    const int invit_iters = g_invit_iters;
+    for (int iter = 0; iter < invit_iters; iter++) {
         if (warp < 8 && lane == 0) {
             const int w = warp;
             const double l = lam[w];
@@ -638,6 +644,10 @@ static int launch_eig(dmp2_engine* e, const float* m, int L, int rows_in_smem, i
 int run_eig_top8(dmp2_engine* e, const float* m, int L, float* vals, float* mds_scaled, float* vecs_raw, cudaStream_t st) {
     constexpr size_t LIMIT = 216 * 1024;
     if (!e->attr_eig) {
+        if (getenv("DMP2_EIG_INVIT") && atoi(getenv("DMP2_EIG_INVIT")) >= 1) {
+            const int it = atoi(getenv("DMP2_EIG_INVIT"));
+            CUDA_TRY(e, cudaMemcpyToSymbol(g_invit_iters, &it, sizeof(int)));
+        }
         CUDA_TRY(e, cudaFuncSetAttribute(k_eig_top8<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LIMIT));
         CUDA_TRY(e, cudaFuncSetAttribute(k_eig_top8<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LIMIT));
         CUDA_TRY(e, cudaFuncSetAttribute(k_eig_top8<16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));

@@ -55,6 +55,17 @@ static int pack_bigru(dmp2_engine* e, HostSD& sd, const std::string& prefix, int
     out->K = K;
     TRY(upload(e, wih, &out->w_ih));
     TRY(upload(e, bih, &out->b_ih));
+    const int Kp = (K + 63) & ~63;
+    std::vector<__half> wh((size_t)1536 * Kp, __float2half_rn(0.f)), wl(wh);
+    for (int r = 0; r < 1536; r++)
+        for (int k = 0; k < K; k++) {
+            const float v = wih[(size_t)r * K + k] * DMP2_GRU_SW;
+            const __half h = __float2half_rn(v);
+            wh[(size_t)r * Kp + k] = h;
+            wl[(size_t)r * Kp + k] = __float2half_rn(v - __half2float(h));
+        }
+    TRY(upload(e, wh, &out->w_ih_hi));
+    TRY(upload(e, wl, &out->w_ih_lo));
     return 0;
 }
 

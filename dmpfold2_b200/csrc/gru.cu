@@ -195,14 +195,47 @@ k_bigru_rec(const float* __restrict__ gi, const float* __restrict__ whh_f, const
     cluster.sync();                                   // nobody exits while a peer could still be storing into it
 }
 
+// layer input [L][k1 (+ k2)] * DMP2_GRU_SA -> fp16 hi/lo [L][Kp] (zero-padded), the A operand of the tensor-core projection
+__global__ void __launch_bounds__(256) k_gru_operand(const float* __restrict__ p1, int ld1, int k1, const float* __restrict__ p2, int ld2,
+                                                     int k2, int L, int Kp, __half* __restrict__ hi, __half* __restrict__ lo) {
+    const int n = L * Kp;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+        const int r = idx / Kp, k = idx - r * Kp;
+        float v = 0.f;
+        if (k < k1) v = p1[(int64_t)r * ld1 + k];
+        else if (k < k1 + k2) v = p2[(int64_t)r * ld2 + (k - k1)];
+        v *= DMP2_GRU_SA;
+        const __half h = __float2half_rn(v);
+        hi[idx] = h;
+        lo[idx] = __float2half_rn(v - __half2float(h));
+    }
+}
+
+// gi = x W_ih^T + b_ih on the tcgen05 GEMM (3 MMAs per MAC, chains of 128)
+static int gru_project_tc(dmp2_engine* e, const BiGruLayer& ly, const float* p1, int ld1, int k1, const float* p2, int ld2, int k2,
+                          int L, cudaStream_t st) {
+    const int Kp = (ly.K + 63) & ~63;
+    __half* a_hi = e->ws.tc_scratch;
+    __half* a_lo = a_hi + (int64_t)L * Kp;
+    k_gru_operand<<<std::min(cdiv(L * Kp, 256), e->num_sms * 4), 256, 0, st>>>(p1, ld1, k1, p2, ld2, k2, L, Kp, a_hi, a_lo);
+    POST_LAUNCH(e, "k_gru_operand");
+    GemmTcEpilogue ep{0, 0, nullptr, nullptr, nullptr};
+    ep.bias = ly.b_ih;
+    return run_gemm_tc(e, a_hi, a_lo, ly.w_ih_hi, ly.w_ih_lo, L, 1536, Kp, 1.0f / (DMP2_GRU_SA * DMP2_GRU_SW), e->ws.gi, 1536, 128, st, &ep);
+}
+
 template <class AL>
-static int bigru_stack(dmp2_engine* e, const BiGruLayer* layers, int nlayers, AL first, int L, float* out, cudaStream_t st) {
+static int bigru_stack(dmp2_engine* e, const BiGruLayer* layers, int nlayers, AL first, int L, float* out, cudaStream_t st,
+                       const float* in1 = nullptr, int ld1 = 0, int k1 = 0, const float* in2 = nullptr, int ld2 = 0, int k2 = 0) {
     Workspace& ws = e->ws;
     float* bufs[2] = {ws.seq_a, ws.seq_b};
     const float* prev = nullptr;
     for (int k = 0; k < nlayers; k++) {
         const BiGruLayer& ly = layers[k];
-        if (k == 0)
+        if (e->gemm_tc && in1 && L <= DMP2_TC_SLAB) {
+            if (k == 0) TRY(gru_project_tc(e, ly, in1, ld1, k1, in2, ld2, k2, L, st));
+            else TRY(gru_project_tc(e, ly, prev, 512, 512, nullptr, 0, 0, L, st));
+        } else if (k == 0)
             sgemm_launch<4>(L, 1536, ly.K, first, LoadRowMajorK{ly.w_ih, ly.K}, StoreRowMajor{ws.gi, 1536, ly.b_ih, 1.0f}, st);
         else
             sgemm_launch<4>(L, 1536, ly.K, LoadRowMajorK{prev, 512}, LoadRowMajorK{ly.w_ih, ly.K},
@@ -217,7 +250,7 @@ static int bigru_stack(dmp2_engine* e, const BiGruLayer* layers, int nlayers, AL
 }
 
 int run_bigru(dmp2_engine* e, const BiGruLayer* layers, int nlayers, const float* in, int L, float* out, cudaStream_t st) {
-    return bigru_stack(e, layers, nlayers, LoadRowMajorK{in, layers[0].K}, L, out, st);
+    return bigru_stack(e, layers, nlayers, LoadRowMajorK{in, layers[0].K}, L, out, st, in, layers[0].K, layers[0].K);
 }
 
 // ca[t][d] = sum_k h[t][k] * W[d][k]                                                  (network.py:255)
@@ -242,7 +275,7 @@ int run_coord_head(dmp2_engine* e, const float* mat1d_t, const float* mds, int L
     float* gout = e->ws.seq_a;     // last layer output; layers 0,1 ping-pong seq_a/seq_b, layer 2 (k&1==0) would alias
     // bigru_stack writes layer k into bufs[k&1] except the last which goes to `out`; use seq_b-safe target:
     gout = e->ws.v_last;           // [L][512] scratch, free after hgru
-    TRY(bigru_stack(e, e->w.cgru, 3, LoadConcat2{mat1d_t, 512, 512, mds, 8}, L, gout, st));
+    TRY(bigru_stack(e, e->w.cgru, 3, LoadConcat2{mat1d_t, 512, 512, mds, 8}, L, gout, st, mat1d_t, 512, 512, mds, 8, 8));
     k_coord_fc<<<cdiv(L, 4), 128, 0, st>>>(gout, e->w.coord_fc, L, ca);
     POST_LAUNCH(e, "k_coord_fc");
     return 0;
