@@ -61,6 +61,25 @@ def fold_many(targets: Sequence, fold_fn: Callable[[object], object], gather: bo
     return [merged[t] for t in range(len(targets))]
 
 
+def fold_many_batched(targets: Sequence, batch_fn: Callable[[List[object]], List[object]], gather: bool = True) -> List[object]:
+    """Like fold_many, but the rank's shard is handed to `batch_fn` in ONE call (e.g. StreamPool.fold_all, which keeps
+    several targets in flight on the GPU); batch_fn returns one result per local target, in order."""
+    rank, ws = world()
+    mine = targets_for_rank(len(targets), rank, ws)
+    res = batch_fn([targets[t] for t in mine]) if mine else []
+    if len(res) != len(mine):
+        raise RuntimeError('batch_fn returned %d results for %d targets' % (len(res), len(mine)))
+    local = dict(zip(mine, res))
+    if ws == 1 or not gather:
+        return [local.get(t) for t in range(len(targets))]
+    parts: List[Optional[dict]] = [None] * ws
+    dist.all_gather_object(parts, local)
+    merged = {}
+    for p in parts:
+        merged.update(p)
+    return [merged[t] for t in range(len(targets))]
+
+
 class StreamPool:
     """Throughput mode on ONE GPU: K engines on K CUDA streams fold independent targets concurrently
     (BASELINE.json configs[2]: "one target per stream").

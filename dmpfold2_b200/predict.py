@@ -159,20 +159,52 @@ def aln_to_coords(input_file, device=default_device, template=None, iterations=d
     return coords, confs
 
 
+_POOLS: Dict[Tuple[str, int, int], object] = {}
+
+
 def alns_to_coords(input_files, device='cuda', templates=None, iterations=default_iterations, minsteps=default_minsteps,
-                   weights_file=None, gather=True):
+                   weights_file=None, gather=True, streams=1):
     """Batch form of aln_to_coords for many independent alignments (BASELINE.json configs[2]).  Under
     torch.distributed (one process per GPU) the list is sharded round-robin over the ranks with no data-path
-    collective (dmpfold2_b200.parallel.fold_many); results come back as CPU tensors in input order."""
-    from .parallel import fold_many
+    collective (dmpfold2_b200.parallel); results come back as CPU tensors in input order.
+    streams > 1: throughput mode -- every rank keeps `streams` targets in flight on its GPU (one engine + one CUDA stream
+    each, parallel.StreamPool), so the latency-bound stages of one target run beside the convs of another."""
+    from .parallel import StreamPool, fold_many, fold_many_batched
     templates = templates or [None] * len(input_files)
+    if streams <= 1:
+        def one(job):
+            path, tmpl = job
+            coords, confs = aln_to_coords(path, device=device, template=tmpl, iterations=iterations, minsteps=minsteps,
+                                          weights_file=weights_file)
+            return coords.cpu(), confs.cpu()
+        return fold_many(list(zip(input_files, templates)), one, gather=gather)
 
-    def one(job):
-        path, tmpl = job
-        coords, confs = aln_to_coords(path, device=device, template=tmpl, iterations=iterations, minsteps=minsteps,
-                                      weights_file=weights_file)
-        return coords.cpu(), confs.cpu()
-    return fold_many(list(zip(input_files, templates)), one, gather=gather)
+    dev_index = _compute_device(torch.device(device))
+    key = (os.path.realpath(weights_file) if weights_file else '<default>', dev_index, int(streams))
+    pool = _POOLS.get(key)
+    if pool is None:
+        pool = _POOLS[key] = StreamPool(load_weights(weights_file), dev_index, streams=int(streams))
+
+    def batch(jobs):
+        msas, tms = [], []
+        for path, tmpl in jobs:
+            alnmat = encode_aln(read_aln(path))
+            if np.any(alnmat > 21):
+                raise ValueError('alignment contains characters outside the residue alphabet')
+            t = None
+            if tmpl is not None:
+                t = read_template(tmpl)
+                if t.shape[0] != alnmat.shape[1]:
+                    raise RuntimeError(f'Sizes of tensors must match: template has {t.shape[0]} CA atoms, '
+                                       f'alignment has {alnmat.shape[1]} columns')
+                t = torch.from_numpy(t)
+            msas.append(torch.from_numpy(np.ascontiguousarray(alnmat)))
+            tms.append(t)
+        with torch.cuda.device(dev_index):
+            out = pool.fold_all(msas, tms, max(iterations, 0), max(minsteps, 0))
+            torch.cuda.synchronize()
+        return [(c.cpu(), f.cpu()) for c, f in out]
+    return fold_many_batched(list(zip(input_files, templates)), batch, gather=gather)
 
 
 def confidence_summary(confs, threshold: float = 0.5) -> Dict[str, float]:

@@ -173,6 +173,10 @@ def test_batch_api(pf10963, tmp_path):
     assert len(res) == 2 and res[0][0].shape == (82, 5, 3) and res[1][0].shape == (40, 5, 3)
     c, f = aln_to_coords(str(short), device='cuda:0', iterations=1, minsteps=5)
     assert torch.equal(res[1][0], c.cpu()) and torch.equal(res[1][1], f.cpu())
+    # throughput mode: three targets in flight on two streams give the same bits as one at a time
+    res2 = alns_to_coords([aln, str(short), aln], device='cuda:0', iterations=1, minsteps=5, streams=2)
+    assert len(res2) == 3 and torch.equal(res2[0][0], res[0][0]) and torch.equal(res2[1][1], res[1][1])
+    assert torch.equal(res2[2][0], res[0][0])
 
 
 @needs_weights

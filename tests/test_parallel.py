@@ -23,6 +23,7 @@ def test_round_robin_shards_partition_the_targets():
     assert P.max_over_ranks(3.5) == 3.5
     assert P.fold_many([1, 2, 3], lambda t: t * 10) == [10, 20, 30]
     assert P.exchange_handles(b'x' * 64) == [b'x' * 64]
+    assert P.fold_many_batched([1, 2, 3], lambda ts: [t * 10 for t in ts]) == [10, 20, 30]
 
 
 def test_stream_pool_host_logic():
@@ -74,6 +75,10 @@ def _worker(rank, world_size, port, out_dir):
         assert [r['target'] for r in res] == [0, 1, 2, 3, 4]
         assert [r['rank'] for r in res] == [0, 1, 0, 1, 0]
         assert all(float(r['coords'][0, 0, 0]) == r['target'] for r in res)
+        resb = P.fold_many_batched(list(range(5)), lambda ts: [fake_fold(t) for t in ts])
+        assert [r['target'] for r in resb] == [0, 1, 2, 3, 4] and [r['rank'] for r in resb] == [0, 1, 0, 1, 0]
+        calls.clear()
+        calls.extend(P.targets_for_rank(5, rank, world_size))
         local = P.fold_many(list(range(5)), fake_fold, gather=False)
         assert [x is not None for x in local] == [t % world_size == rank for t in range(5)]
         handles = P.exchange_handles(bytes([rank]) * 64)                  # the one-off window-handle exchange of a StripGroup
