@@ -180,6 +180,7 @@ def main():
     ap.add_argument('--impl', type=str, default='engine')
     ap.add_argument('--conv-mode', type=str, default='f16f8', choices=['f16f8', 'f16x3', 'f16', 'ffma'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extras', action='store_true', help='skip the informational sections (other conv modes, throughput mode)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
@@ -264,7 +265,7 @@ def main():
     # ---- informational: the other conv modes (f16x3 = reference-accuracy conv, 3 MMAs per MAC; f16 = single fp16 MMA,
     # which does NOT hold the parity bar)
     fast_ms = {}
-    if args.conv_mode == 'f16f8':
+    if args.conv_mode == 'f16f8' and not args.no_extras:
         for fm in ('f16x3', 'f16'):
             eng.set_conv_mode(fm)
             eng.fold(msas_dev[0], None, N_ITER, N_MIN)
@@ -283,7 +284,7 @@ def main():
     tp_ms = {}
     try:
         from dmpfold2_b200.parallel import StreamPool
-        for k_streams, conv_sms in ((2, 0), (3, 0), (3, 132)):
+        for k_streams, conv_sms in (() if args.no_extras else ((2, 0), (3, 0), (3, 132))):
             pool = StreamPool(sd, local_rank, streams=k_streams, conv_mode=args.conv_mode, conv_sms=conv_sms)
             n_tp = max(k_streams * 2, (args.steps // k_streams) * k_streams)
             idx = [args.warmup + (k % args.steps) for k in range(n_tp)]

@@ -441,7 +441,14 @@ int dmp2_create(dmp2_engine** out, int device, int n_tensors, const char* const*
         return s;
     }
     for (int i = 0; i < 16; i++) cudaEventCreate(&e->ev[i]);
-    cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking);
+    {   // The MSA features run beside the vgru; the vgru is the critical path (1000 dependent steps that each want the
+        // whole GPU), so the side stream gets the LOWEST priority: its kernels fill SMs only when no vgru CTA is pending.
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        const char* sp = getenv("DMP2_SIDE_PRIORITY");
+        if (sp && !strcmp(sp, "default")) cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking);
+        else cudaStreamCreateWithPriority(&e->side, cudaStreamNonBlocking, lo);
+    }
     cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming);
     e->ev_ok = true;
