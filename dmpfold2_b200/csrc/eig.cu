@@ -385,7 +385,6 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
         }
     }
 
-    __shared__ double wy_y[8][16], wy_w[8][16], wy_g[16][17];        // blocked back-transformation scratch
     stamp(3);
     // ---------------- 4. back-transform: z <- H_0 H_1 ... H_{n-3} z  (warp w owns vector w) --------------
     // Reflectors are staged `stage_rows` at a time into shared memory by all warps (one L2 round trip per block
@@ -402,96 +401,23 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
                 if (i < n - (klo + r) - 1) stage[idx] = __ldcg(V + (int64_t)(klo + r) * n + i);
             }
             __syncthreads();
-            // Blocked (compact WY) application of the nb = khi - klo + 1 staged reflectors:
-            //   H_klo ... H_khi = I - V T V^T  with  T^-1 = diag(1/beta) + striu(V^T V)   (beta_i = 2 / v_i^T v_i),
-            // so  z <- z - V w  where  w solves  (diag(1/beta) + striu(G)) w = V^T z  by back substitution.
-            // Instead of nb dependent dot-product/update round trips per vector there are two phases per block:
-            //   A: warps 0..7 form y = V^T z for their vector, warps 8..15 the Gram entries G[r][s] (r < s);
-            //   B: one lane per vector solves the nb x nb triangular system, the warp applies z -= V w.
-            // Block row j <-> matrix row klo + 1 + j; reflector r is zero for j < r and v_r[j] = stage[r*n + j - r].
-            {
-                const int nb = khi - klo + 1, mb = n - klo - 1;
-                if (warp < 8) {
-                    const double* zz = zs + warp * n + klo + 1;
-                    for (int r0 = 0; r0 < nb; r0 += 4) {
-                        double acc[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-                        for (int u = 0; u < 4; u++) {
-                            const int r = r0 + u;
-                            if (r < nb) {
-                                const double* v = stage + r * n;
-                                const int m = mb - r;
-                                double a = 0.0;
-                                for (int i = lane; i < m; i += 32) a += v[i] * zz[i + r];
-                                acc[u] = a;
-                            }
-                        }
-#pragma unroll
-                        for (int o = 16; o; o >>= 1) {
-#pragma unroll
-                            for (int u = 0; u < 4; u++) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
-                        }
-                        if (lane < 4 && r0 + lane < nb) wy_y[warp][r0 + lane] = acc[lane];
-                    }
-                } else {
-                    const int npairs = nb * (nb - 1) / 2;
-                    for (int p0 = (warp - 8) * 4; p0 < npairs; p0 += 32) {       // 4 pairs per warp per round, 8 warps
-                        double acc[4] = {0.0, 0.0, 0.0, 0.0};
-                        int rr[4], ss[4];
-#pragma unroll
-                        for (int u = 0; u < 4; u++) {
-                            int p = p0 + u;
-                            rr[u] = -1; ss[u] = -1;
-                            if (p < npairs) {
-                                int sidx = 1;                                   // pair p -> (r, s), r < s, enumerated by s then r
-                                while (p >= sidx) { p -= sidx; sidx++; }
-                                rr[u] = p; ss[u] = sidx;
-                                const double* vr = stage + rr[u] * n + (ss[u] - rr[u]);
-                                const double* vs = stage + ss[u] * n;
-                                const int m = mb - ss[u];
-                                double a = 0.0;
-                                for (int i = lane; i < m; i += 32) a += vr[i] * vs[i];
-                                acc[u] = a;
-                            }
-                        }
-#pragma unroll
-                        for (int o = 16; o; o >>= 1) {
-#pragma unroll
-                            for (int u = 0; u < 4; u++) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
-                        }
-                        if (lane < 4 && rr[lane] >= 0) wy_g[rr[lane]][ss[lane]] = acc[lane];
-                    }
-                }
-                __syncthreads();
-                if (warp < 8) {
-                    if (lane == 0) {
-                        double w[16];
-#pragma unroll
-                        for (int i = 15; i >= 0; i--) {
-                            w[i] = 0.0;
-                            if (i < nb) {
-                                double t = wy_y[warp][i];
-#pragma unroll
-                                for (int c = 15; c > i; c--)
-                                    if (c < nb) t -= wy_g[i][c] * w[c];
-                                w[i] = beta[klo + i] * t;
-                            }
-                        }
-#pragma unroll
-                        for (int i = 0; i < 16; i++) wy_w[warp][i] = w[i];
-                    }
+            if (warp < 8) {
+                double* z = zs + warp * n;
+                for (int k = khi; k >= klo; k--) {
+                    const double bt = beta[k];
+                    if (bt == 0.0) continue;
+                    const int m = n - k - 1;
+                    const double* v = stage + (k - klo) * n;
+                    double* zz = z + k + 1;
+                    double a = 0.0, a2 = 0.0;
+                    int i = lane;
+#pragma unroll 2
+                    for (; i + 32 < m; i += 64) { a += v[i] * zz[i]; a2 += v[i + 32] * zz[i + 32]; }
+                    if (i < m) a += v[i] * zz[i];
+                    a = warp_sum(a + a2) * bt;
+#pragma unroll 4
+                    for (i = lane; i < m; i += 32) zz[i] -= a * v[i];
                     __syncwarp();
-                    double* zz = zs + warp * n + klo + 1;
-                    double w[16];
-#pragma unroll
-                    for (int i = 0; i < 16; i++) w[i] = i < nb ? wy_w[warp][i] : 0.0;
-                    for (int j = lane; j < mb; j += 32) {
-                        double a = 0.0;
-#pragma unroll
-                        for (int r = 0; r < 16; r++)
-                            if (r < nb && r <= j) a += stage[r * n + (j - r)] * w[r];
-                        zz[j] -= a;
-                    }
                 }
             }
             __syncthreads();
