@@ -155,6 +155,7 @@ struct Workspace {
     double* stat_part = nullptr;   // [nparts][256] partial sums
     float* norm_ss = nullptr;      // [256] per-channel scale, shift
     unsigned int* ticket = nullptr;
+    unsigned long long* sched = nullptr;       // unit counter of the dynamic conv schedule
     float* head = nullptr;         // [2][L*L]
     float* conf = nullptr;         // [L]
     float* mmat = nullptr;         // [L*L]
@@ -217,6 +218,11 @@ struct dmp2_engine {
     void* vt_state = nullptr;        // tensor-core vgru state, owned by vgru_tc.cu
     int conv_cluster = 0;            // conv kernel form: 0 = cta_group::2 CTA pairs, 1 = independent CTAs, 2 = 2-CTA weight multicast (DMP2_CONV_CLUSTER=pair|1|2)
     int conv_sms = 0;                // SMs the persistent conv kernel occupies (0 = all)
+    const float* vgru_pre = nullptr; // one-shot: the next dmp2_fold takes the vgru state [L][512] from here instead of scanning the MSA
+                                     // (dmp2_set_vgru_input; a throughput scheduler scans the columns of several targets in ONE vgru call)
+    bool conv_dynamic = false;       // conv units claimed from a global counter instead of the static round-robin (throughput mode:
+                                     // several folds in flight on one GPU; dmp2_set_conv_dynamic / DMP2_CONV_DYNAMIC=1)
+    unsigned long long conv_sched_base = 0;      // first counter value of the next dynamic conv launch (ws.sched is never reset)
     int conv_chunk_taps = 0;         // taps per tcgen05 accumulation chain (1, 5 or 25; DMP2_CONV_CHUNK); 0 = per mode: 1 for f16x3 (whose
                                      // operands are exact to 2^-22, so the chain length IS its error), 5 for f16f8 / f16 (operand error 6e-6 / 1e-4
                                      // dwarfs the 6e-7 of a 5-tap chain; 2-3 % faster)

@@ -100,8 +100,16 @@ struct TcParams {
     const float* gamma;
     double* totals;              // halo-sharded: [sum 128 | sumsq 128] of this launch instead of norm
     double npix;                 // pixels the statistics are over (H * L)
+    // dynamic unit scheduler (throughput mode, several folds in flight on one GPU): nullptr = the static round-robin
+    // schedule; otherwise the clusters claim units from a global counter, so a launch that only gets part of the SMs
+    // (the others are busy with another stream's kernels) is finished by the CTAs that did start, and CTAs that
+    // become resident late find nothing left and exit.  The counter is never reset: launch k owns the values
+    // [sched_base, sched_base + units + clusters) (every cluster makes exactly one failing claim).
+    unsigned long long* sched;
+    unsigned long long sched_base;
 };
 constexpr int STAT_GROUP = 16;   // CTAs per first-level fold
+constexpr int UQ = 4;            // depth of the claimed-unit queue (the roles of a cluster are never 4 units apart, see unit_at)
 
 using namespace tc;
 
@@ -192,6 +200,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv5_tc(const __grid_consta
     auto c_full = [&](int s) { return bar_base + 8u * (2 * NS + s); };
     auto c_empty = [&](int s) { return bar_base + 8u * (2 * NS + 2 + s); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * NS + 4);
+    auto uq_full = [&](int s) { return bar_base + 8u * (2 * NS + 5 + s); };
+    auto uq_val = [&](int s) { return bar_base + 8u * (2 * NS + 5 + UQ) + 4u * s; };
+    static_assert(8 * (2 * NS + 5 + UQ) + 4 * UQ <= 256, "barrier area");
     uint8_t* smem_gen = smem_raw + (base - smem_u32(smem_raw));
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - base));
 
@@ -207,6 +218,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv5_tc(const __grid_consta
         for (int s = 0; s < NS; s++) { mbar_init(full(s), 1); mbar_init(empty(s), PAIR ? 1 : CL); }
         // pair: the leader's issuer waits for the epilogue warps of BOTH CTAs before it reuses a chunk accumulator
         for (int s = 0; s < 2; s++) { mbar_init(c_full(s), 1); mbar_init(c_empty(s), PAIR ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS); }
+        for (int s = 0; s < UQ; s++) mbar_init(uq_full(s), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -226,6 +238,32 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv5_tc(const __grid_consta
     if (CL > 1) cluster_sync_all();                  // peers' barriers must be initialised before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
+    // The i-th unit of this cluster (>= p.units: no more work).  Static schedule: round-robin over the clusters.  Dynamic:
+    // rank 0's producer warp claims units from the global counter and posts each one into the queue slot i % UQ of
+    // EVERY CTA of the cluster (st.async + expect_tx on that CTA's mbarrier: value and signal in one DSMEM operation);
+    // all roles of all CTAs read the same sequence.  No "slot free" handshake is needed: the producer is at most a ring
+    // of stages ahead of the issuer and the issuer at most two chunks ahead of the epilogue, so unit i + UQ is claimed
+    // long after every role has read unit i.
+    const bool dyn = p.sched != nullptr;
+    auto unit_at = [&](int i) -> int {
+        if (!dyn) return cluster_id + i * num_clusters;
+        mbar_wait(uq_full(i & (UQ - 1)), (uint32_t)(i / UQ) & 1u);
+        int v;
+        asm volatile("ld.volatile.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(uq_val(i & (UQ - 1))) : "memory");
+        return v;
+    };
+    auto claim = [&]() -> unsigned long long { return atomicAdd(p.sched, 1ULL); };     // one lane; consumed much later (post_unit)
+    auto post_unit = [&](int i, unsigned long long raw) {                                // one lane of rank 0's producer warp
+        const unsigned long long rel = raw - p.sched_base;
+        const int v = rel < (unsigned long long)p.units ? (int)rel : p.units;
+#pragma unroll
+        for (int rk = 0; rk < CL; rk++) {
+            const uint32_t rb = CL > 1 ? mapa_u32(uq_full(i & (UQ - 1)), rk) : uq_full(i & (UQ - 1));
+            const uint32_t rv = CL > 1 ? mapa_u32(uq_val(i & (UQ - 1)), rk) : uq_val(i & (UQ - 1));
+            asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], 4;" ::"r"(rb) : "memory");
+            asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(rv), "r"(v), "r"(rb) : "memory");
+        }
+    };
     // register re-distribution between the warpgroups (the epilogue holds 128 running sums per thread).  The CTA is
     // launched with 168 registers x 384 threads = 64512; 128 x 56 + 256 x 224 uses exactly that pool (asking for more
     // would block setmaxnreg.inc forever).
@@ -235,7 +273,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv5_tc(const __grid_consta
         // ===================== TMA producer (whole warp, one elected lane issues) =====================
         {
             int st = 0, ph = 0;
-            for (int cu = cluster_id; cu < p.units; cu += num_clusters) {
+            const bool claimer = dyn && leader && lane == 0;
+            if (claimer) post_unit(0, claim());
+            __syncwarp();
+            for (int ui = 0;; ui++) {
+                const int cu = unit_at(ui);
+                if (cu >= p.units) break;
+                unsigned long long nxt = 0;
+                if (claimer) nxt = claim();                    // next unit: the atomic's latency hides behind this unit's loads
                 const Unit u = decode_unit<CL>(p, cu, crank);
                 for (int kb = 0; kb < p.num_kb; kb++) {
                     const int tap = kb >> 1, sub = kb & 1;
@@ -299,6 +344,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv5_tc(const __grid_consta
                     __syncwarp();
                     if (++st == NS) { st = 0; ph ^= 1; }
                 }
+                if (claimer) post_unit(ui + 1, nxt);
+                __syncwarp();
             }
         }
     } else if (warp == 1) {
@@ -328,7 +375,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv5_tc(const __grid_consta
             };
             int st = 0, ph = 0;
             uint32_t cc = 0;                                      // chunk counter over the whole kernel: buffer cc & 1
-            for (int cu = cluster_id; cu < p.units; cu += num_clusters) {
+            for (int ui = 0; unit_at(ui) < p.units; ui++) {
                 for (int kb = 0; kb < p.num_kb; kb++) {
                     const int sub = kb & 1;
                     const int in_chunk = kb % p.chunk_kb;
@@ -369,7 +416,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv5_tc(const __grid_consta
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(hcol * 128);
         double st_s[2] = {0.0, 0.0}, st_q[2] = {0.0, 0.0};        // per column tile: this lane's channel, summed over all units
         uint32_t cc = 0;
-        for (int cu = cluster_id; cu < p.units; cu += num_clusters) {
+        for (int ui = 0;; ui++) {
+            const int cu = unit_at(ui);
+            if (cu >= p.units) break;
             const Unit u = decode_unit<CL>(p, cu, crank);
             float R[128];
             for (int ch = 0; ch < chunks_per_unit; ch++, cc++) {
@@ -606,6 +655,10 @@ int launch_mode(dmp2_engine* e, int mode, int form, const ConvMaps& maps, TcPara
     int sms = e->conv_sms > 0 ? std::min(e->conv_sms, e->num_sms) : e->num_sms;
     int grid = std::min(sms / cl, p.units) * cl;
     if (grid < cl) grid = cl;
+    if (p.sched) {                                   // this launch owns the next units + clusters counter values
+        p.sched_base = e->conv_sched_base;
+        e->conv_sched_base += (unsigned long long)p.units + (unsigned long long)(grid / cl);
+    }
     if (mode == DMP2_CONV_TC_F16X3) return launch_form<M_F16X3>(e, form, maps, p, grid, st);
     if (mode == DMP2_CONV_TC_F16F8) return launch_form<M_F16F8>(e, form, maps, p, grid, st);
     return launch_form<M_F16>(e, form, maps, p, grid, st);
@@ -648,6 +701,7 @@ int run_conv_tc(dmp2_engine* e, int blk, const __half* xh, const __half* xl, con
     p.M = H * L; p.N = 512; p.ldc = 512; p.alpha = 1.0f; p.ep = 0; p.m_off = 0; p.dsa = nullptr; p.dsb = nullptr; p.scal = nullptr;
     p.n_tiles_n = 2; p.out = raw; p.bias = bw.bias;
     p.stat_part = nullptr; p.ticket = nullptr; p.norm = nullptr; p.gamma = nullptr; p.totals = nullptr; p.npix = 0;
+    p.sched = e->conv_dynamic ? e->ws.sched : nullptr; p.sched_base = 0;
     if (fuse_stats) {
         p.stat_part = e->ws.stat_part; p.ticket = e->ws.ticket; p.norm = e->ws.norm_ss; p.gamma = bw.gamma;
         p.totals = e->strip_on ? e->sp.totals : nullptr;
@@ -696,6 +750,7 @@ int run_gemm_tn_test(dmp2_engine* e, const float* a, const float* b, int M, int 
         p.gemm = 1; p.L = 0; p.H = 0; p.y_off = 0; p.tiles_x = 1; p.num_kb = K / KCHUNK; p.chunk_kb = chunk_k / KCHUNK;
         p.M = M; p.N = N; p.ldc = N; p.alpha = 1.0f; p.ep = 0; p.m_off = 0; p.dsa = nullptr; p.dsb = nullptr; p.scal = nullptr;
         p.n_tiles_n = cdiv(N, TILE_N); p.out = c; p.bias = nullptr;
+        p.sched = (e->conv_dynamic && e->ws.sched) ? e->ws.sched : nullptr; p.sched_base = 0;      // (after dmp2_reserve: exercises the dynamic schedule)
         p.stat_part = nullptr; p.ticket = nullptr; p.norm = nullptr; p.gamma = nullptr; p.totals = nullptr; p.npix = 0;
         rc = launch_mode(e, mode, e->conv_cluster, maps, p, cdiv(M, TILE_M), st);
     } while (0);
@@ -791,6 +846,7 @@ int run_gemm_tc(dmp2_engine* e, const __half* a_hi, const __half* a_lo, const __
     TcParams p;
     p.gemm = 1; p.L = 0; p.H = 0; p.y_off = 0; p.tiles_x = 1; p.num_kb = Kp / KCHUNK; p.chunk_kb = ck / KCHUNK;
     p.M = M; p.N = N; p.ldc = ldc; p.alpha = alpha; p.n_tiles_n = cdiv(N, TILE_N); p.out = c; p.bias = nullptr;
+    p.sched = nullptr; p.sched_base = 0;
     p.ep = ep ? ep->kind : 0; p.m_off = ep ? ep->m_off : 0; p.dsa = ep ? ep->dsa : nullptr; p.dsb = ep ? ep->dsb : nullptr; p.scal = ep ? ep->scal : nullptr;
     p.bias = ep ? ep->bias : nullptr;
     p.stat_part = nullptr; p.ticket = nullptr; p.norm = nullptr; p.gamma = nullptr; p.totals = nullptr; p.npix = 0;

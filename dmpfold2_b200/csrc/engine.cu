@@ -311,6 +311,9 @@ int ensure_workspace(dmp2_engine* e, int L, int N, int rows2d) {
     TRY(wsalloc(e, &ws.norm_ss, 256));
     TRY(wsalloc(e, &ws.ticket, 64 + stat_grps));
     CUDA_TRY(e, cudaMemset(ws.ticket, 0, (64 + stat_grps) * sizeof(unsigned int)));
+    TRY(wsalloc(e, &ws.sched, 2));
+    CUDA_TRY(e, cudaMemset(ws.sched, 0, 2 * sizeof(unsigned long long)));
+    e->conv_sched_base = 0;
     TRY(wsalloc(e, &ws.head, 2 * P));
     TRY(wsalloc(e, &ws.conf, L));
     TRY(wsalloc(e, &ws.mmat, P));
@@ -378,9 +381,13 @@ static int fold_impl(dmp2_engine* e, const uint8_t* msa, int N, int L, const flo
         const int cper = cdiv(L, sp.world), c0 = std::min(L, sp.rank * cper), c1 = std::min(L, c0 + cper);
         if (c1 > c0) TRY(run_vgru_tc(e, msa + c0, N, c1 - c0, v_last + (int64_t)c0 * 512, st, L));
         TRY(strip_vgru_gather(e, c0, c1, st));
+    } else if (e->vgru_pre && !e->strip_on) {
+        // the scan was done elsewhere (one call over the columns of several targets): take its result
+        CUDA_TRY(e, cudaMemcpyAsync(ws.v_last, e->vgru_pre, (size_t)L * 512 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     } else {
         TRY(run_vgru(e, msa, N, L, ws.v_last, st));
     }
+    e->vgru_pre = nullptr;
     mark();
     TRY(run_bigru(e, e->w.hgru, 2, v_last, L, ws.mat1d_t, st));
     mark();
@@ -466,6 +473,8 @@ int dmp2_create(dmp2_engine** out, int device, int n_tensors, const char* const*
     if (ck && (atoi(ck) == 1 || atoi(ck) == 5 || atoi(ck) == 25)) e->conv_chunk_taps = atoi(ck);
     const char* cs = getenv("DMP2_CONV_SMS");
     if (cs && atoi(cs) > 0) e->conv_sms = atoi(cs);
+    const char* cd = getenv("DMP2_CONV_DYNAMIC");
+    if (cd) e->conv_dynamic = strcmp(cd, "0") != 0;
     const char* vm = getenv("DMP2_VGRU");
     const char* gm = getenv("DMP2_GEMM");
     if (gm && !strcmp(gm, "ffma")) e->gemm_tc = false;
@@ -739,6 +748,18 @@ int dmp2_gemm_tn_test(dmp2_engine* e, const float* a_dev, const float* b_dev, in
     if (!e) return DMP2_ERR_BAD_ARG;
     TRY(check_device(e));
     return run_gemm_tn_test(e, a_dev, b_dev, M, N, K, mode, chunk_k, c_dev, (cudaStream_t)stream);
+}
+
+int dmp2_set_vgru_input(dmp2_engine* e, const float* vgru_dev) {
+    if (!e) return DMP2_ERR_BAD_ARG;
+    e->vgru_pre = vgru_dev;
+    return 0;
+}
+
+int dmp2_set_conv_dynamic(dmp2_engine* e, int on) {
+    if (!e) return DMP2_ERR_BAD_ARG;
+    e->conv_dynamic = on != 0;
+    return 0;
 }
 
 int dmp2_set_conv_sms(dmp2_engine* e, int sms) {

@@ -56,6 +56,8 @@ _SIGS = {
     'dmp2_backbone': (_i, [_vp, _vp, _i, _vp, _vp]),
     'dmp2_gemm_tn_test': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     'dmp2_set_conv_sms': (_i, [_vp, _i]),
+    'dmp2_set_conv_dynamic': (_i, [_vp, _i]),
+    'dmp2_set_vgru_input': (_i, [_vp, _vp]),
 }
 EXPORTS = tuple(_SIGS)
 
@@ -179,11 +181,17 @@ class Engine:
 
     # ---- the hot path --------------------------------------------------------------------------
     def fold(self, msa: torch.Tensor, template_ca: Optional[torch.Tensor] = None, iterations: int = 10,
-             minsteps: int = 100) -> Tuple[torch.Tensor, torch.Tensor]:
+             minsteps: int = 100, vgru: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
         """Device tensors in, device tensors out; asynchronous on the current torch stream.
-        msa uint8 (N,L) codes 0..21; template_ca float32 (L,3) or None -> coords (L,5,3), confs (L,)."""
+        msa uint8 (N,L) codes 0..21; template_ca float32 (L,3) or None -> coords (L,5,3), confs (L,).
+        vgru: optional (L,512) float32 device tensor = self.vgru(msa), computed elsewhere (e.g. one scan over the
+        columns of several alignments, parallel.StreamPool); the caller keeps it alive until the fold has run."""
         msa = self._dev(msa, torch.uint8)
         n, l = msa.shape
+        if vgru is not None:
+            if vgru.dtype != torch.float32 or tuple(vgru.shape) != (l, 512) or not vgru.is_contiguous() or vgru.device != self.device:
+                raise ValueError('vgru must be a contiguous float32 (L, 512) tensor on the engine device')
+            self._check(self.lib.dmp2_set_vgru_input(self.h, _ptr(vgru)), 'dmp2_set_vgru_input')
         tm = None
         if template_ca is not None:
             tm = self._dev(template_ca, torch.float32)
@@ -362,3 +370,7 @@ class Engine:
 
     def set_conv_sms(self, sms: int):
         self._check(self.lib.dmp2_set_conv_sms(self.h, int(sms)), 'dmp2_set_conv_sms')
+
+    def set_conv_dynamic(self, on: bool = True):
+        """Dynamic unit schedule of the persistent conv kernel (several folds in flight on one GPU, see dmp2.h)."""
+        self._check(self.lib.dmp2_set_conv_dynamic(self.h, 1 if on else 0), 'dmp2_set_conv_dynamic')

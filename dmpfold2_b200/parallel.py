@@ -10,6 +10,8 @@ stores + flags inside the kernels' stream (csrc/strip.cu) and torch.distributed 
 """
 from __future__ import annotations
 
+import threading
+from concurrent.futures import ThreadPoolExecutor
 from typing import Callable, List, Optional, Sequence, Tuple
 
 import torch
@@ -80,22 +82,51 @@ def fold_many_batched(targets: Sequence, batch_fn: Callable[[List[object]], List
     return [merged[t] for t in range(len(targets))]
 
 
+def scan_batches(shapes: Sequence[Tuple[int, int]], scan_rows: int) -> List[List[int]]:
+    """Which targets share one vgru scan.  shapes[t] = (N, L) of target t.  Consecutive targets (they are in flight at
+    the same time) with the SAME number of sequences N are grouped while their alignment columns together stay within
+    `scan_rows`; groups of one are dropped (such a fold scans its own alignment).  Returns lists of target indices."""
+    groups: List[List[int]] = []
+    cur: List[int] = []
+    cols = 0
+    for t, (n, l) in enumerate(shapes):
+        if cur and (n != shapes[cur[0]][0] or cols + l > scan_rows):
+            groups.append(cur)
+            cur, cols = [], 0
+        if l <= scan_rows:
+            cur.append(t)
+            cols += l
+    if cur:
+        groups.append(cur)
+    return [g for g in groups if len(g) > 1]
+
+
 class StreamPool:
     """Throughput mode on ONE GPU: K engines on K CUDA streams fold independent targets concurrently
     (BASELINE.json configs[2]: "one target per stream").
 
     A single fold is a serial chain in which the tensor-core conv owns the whole GPU ~2/3 of the time and the rest is
-    latency-bound (1000 dependent vgru steps, the eigensolver, the GRUs).  With K targets in flight the latency-bound
-    stages of one target run beside the convs of another.  Every engine has its own workspace; the weights are
-    uploaded once per engine.  `conv_sms` < #SMs keeps a few SMs free of the persistent conv kernel so that the small
-    kernels of the other streams never wait for a whole conv launch to drain.
+    latency-bound (the dependent vgru steps, the eigensolver, the GRUs).  With K targets in flight the small-footprint
+    stages of one target (eigensolver, GRUs, minimiser) run beside the convs of another.  Every engine has its own
+    workspace; the weights are uploaded once per engine.
+
+    * conv_dynamic (default: on when streams > 1): the conv kernel claims its work units from a device counter, so a
+      launch that finds SMs occupied by another target's kernels is finished by the CTAs that did start
+      (dmp2_set_conv_dynamic).
+    * scan_rows (default 384 = one wave of the vgru kernel; 0 = off): the vgru scan (network.py:223-224) is N dependent
+      steps that each occupy ~all SMs for ~14 us, mostly waiting, whatever the alignment length up to 384 columns.  It is
+      independent per alignment column, so the pool scans the columns of consecutive targets with the same N in ONE call
+      on a separate engine and hands every fold its slice (dmp2_set_vgru_input): bit-identical, and the scan costs the
+      batch what it used to cost one target.
+    * conv_sms < #SMs keeps a few SMs free of the persistent conv kernel.
 
     engine_factory(i) -> engine lets the CPU tests (and other back ends) substitute the engine; an engine needs
     fold(msa, template, iterations, minsteps) -> (coords, confs), set_conv_sms(n) and close().
     """
 
     def __init__(self, state_dict=None, device_index: int = 0, streams: int = 2, conv_mode: Optional[str] = None,
-                 conv_sms: int = 0, engine_factory: Optional[Callable[[int], object]] = None):
+                 conv_sms: int = 0, engine_factory: Optional[Callable[[int], object]] = None,
+                 conv_dynamic: Optional[bool] = None, scan_rows: int = 384):
         if streams < 1:
             raise ValueError('streams must be >= 1')
         if engine_factory is None:
@@ -104,10 +135,19 @@ class StreamPool:
             def engine_factory(i):
                 return Engine(state_dict, device_index, conv_mode=conv_mode)
         self.device_index = device_index
+        self._factory = engine_factory
         self.engines = [engine_factory(i) for i in range(streams)]
         if conv_sms:
             for e in self.engines:
                 e.set_conv_sms(conv_sms)
+        self.conv_dynamic = (streams > 1) if conv_dynamic is None else bool(conv_dynamic)
+        if self.conv_dynamic:
+            for e in self.engines:
+                if hasattr(e, 'set_conv_dynamic'):
+                    e.set_conv_dynamic(True)
+        self.scan_rows = int(scan_rows)
+        self._scan_engine = None
+        self._scan_stream = None
         self._streams = None
 
     def _cuda_streams(self):
@@ -121,8 +161,8 @@ class StreamPool:
         return [t % len(self.engines) for t in range(num_targets)]
 
     def fold_all(self, msas: Sequence, templates: Optional[Sequence] = None, iterations: int = 10, minsteps: int = 100,
-                 use_cuda_streams: bool = True) -> List[Tuple[object, object]]:
-        """Fold every alignment; returns [(coords, confs)] in input order.  Asynchronous w.r.t. the host until the
+                 use_cuda_streams: bool = True, host_threads: bool = True) -> List[Tuple[object, object]]:
+        """Fold every alignment; returns [(coords, confs)] in input order.  Asynchronous w.r.t. the device until the
         final synchronisation of the streams with the caller's current stream."""
         k = len(self.engines)
         out: List[Optional[Tuple[object, object]]] = [None] * len(msas)
@@ -130,25 +170,101 @@ class StreamPool:
             for t, msa in enumerate(msas):
                 out[t] = self.engines[t % k].fold(msa, None if templates is None else templates[t], iterations, minsteps)
             return out
-        if len(msas) and hasattr(self.engines[0], 'reserve'):        # no allocation (= device sync) inside the folds
-            lmax, nmax = max(int(m.shape[1]) for m in msas), max(int(m.shape[0]) for m in msas)
+        if not len(msas):
+            return out
+        dev = torch.device('cuda', self.device_index)
+        shapes = [(int(m.shape[0]), int(m.shape[1])) for m in msas]
+        if hasattr(self.engines[0], 'reserve'):      # no allocation (= device sync) inside the folds
             for e in self.engines:
-                e.reserve(lmax, nmax)
+                e.reserve(max(l for _, l in shapes), max(n for n, _ in shapes))
         streams = self._cuda_streams()
-        cur = torch.cuda.current_stream(torch.device('cuda', self.device_index))
+        cur = torch.cuda.current_stream(dev)
         for s in streams:
             s.wait_stream(cur)
-        for t, msa in enumerate(msas):
-            with torch.cuda.stream(streams[t % k]):
-                out[t] = self.engines[t % k].fold(msa, None if templates is None else templates[t], iterations, minsteps)
+
+        # ---- shared vgru scans
+        batches = scan_batches(shapes, self.scan_rows) if (self.scan_rows > 0 and hasattr(self.engines[0], 'vgru')) else []
+        batch_of = {t: b for b, g in enumerate(batches) for t in g}
+        scans: List[Optional[tuple]] = [None] * len(batches)          # (state of the whole batch, event, {target: first row})
+        posted = [threading.Event() for _ in batches]
+        failure: List[BaseException] = []
+        if batches:
+            if self._scan_engine is None:
+                self._scan_engine = self._factory(k)
+                self._scan_stream = torch.cuda.Stream(device=dev, priority=-1)   # short chains of whole-GPU steps: let them through
+            self._scan_engine.reserve(max(sum(shapes[t][1] for t in g) for g in batches), max(shapes[g[0]][0] for g in batches))
+            self._scan_stream.wait_stream(cur)
+            msas = [m if (torch.is_tensor(m) and m.device == dev) else torch.as_tensor(m, dtype=torch.uint8).to(dev) for m in msas]
+
+        def enqueue_scans():
+            torch.cuda.set_device(self.device_index)
+            try:
+                with torch.cuda.stream(self._scan_stream):
+                    for b, g in enumerate(batches):
+                        cols = torch.cat([msas[t] for t in g], dim=1).contiguous()       # [N][L1 + L2 + ...]
+                        state = self._scan_engine.vgru(cols)                              # [L1 + L2 + ...][512]
+                        ev = torch.cuda.Event()
+                        ev.record(self._scan_stream)
+                        first, row = {}, 0
+                        for t in g:
+                            first[t] = row
+                            row += shapes[t][1]
+                            state.record_stream(streams[t % k])
+                        scans[b] = (state, ev, first)
+                        posted[b].set()
+            except BaseException as exc:             # never leave a fold thread waiting for a scan that will not come
+                failure.append(exc)
+                for p in posted:
+                    p.set()
+                raise
+
+        def fold_one(i, t):
+            vg = None
+            if t in batch_of:
+                b = batch_of[t]
+                posted[b].wait()
+                if failure:
+                    raise RuntimeError('shared vgru scan failed') from failure[0]
+                state, ev, first = scans[b]
+                streams[i].wait_event(ev)
+                vg = state[first[t]:first[t] + shapes[t][1]]
+            tm = None if templates is None else templates[t]
+            out[t] = self.engines[i].fold(msas[t], tm, iterations, minsteps, vgru=vg) if vg is not None else \
+                self.engines[i].fold(msas[t], tm, iterations, minsteps)
+
+        def enqueue(i):                              # everything stream i folds, in order
+            torch.cuda.set_device(self.device_index)
+            with torch.cuda.stream(streams[i]):
+                for t in range(i, len(msas), k):
+                    fold_one(i, t)
+
+        if k == 1 or not host_threads:
+            if batches:
+                enqueue_scans()
+            for t in range(len(msas)):               # interleaved: consecutive targets are in flight together
+                with torch.cuda.stream(streams[t % k]):
+                    fold_one(t % k, t)
+        else:
+            # One host thread per stream (a fold is several thousand kernel launches; the C calls release the GIL), plus
+            # one for the scans.
+            with ThreadPoolExecutor(max_workers=k + 1) as ex:
+                futs = [ex.submit(enqueue_scans)] if batches else []
+                futs += [ex.submit(enqueue, i) for i in range(k)]
+                for f in futs:
+                    f.result()
         for s in streams:
             cur.wait_stream(s)
+        if batches:
+            cur.wait_stream(self._scan_stream)
         return out
 
     def close(self):
         for e in self.engines:
             e.close()
         self.engines = []
+        if self._scan_engine is not None:
+            self._scan_engine.close()
+            self._scan_engine = None
 
 
 def exchange_handles(handle: bytes) -> List[bytes]:

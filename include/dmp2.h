@@ -170,6 +170,21 @@ int dmp2_gemm_tn_test(dmp2_engine* e, const float* a_dev, const float* b_dev, in
  * targets on several streams leaves a few SMs to the latency-bound kernels of the other targets. */
 int dmp2_set_conv_sms(dmp2_engine* e, int sms);
 
+/* Throughput mode: hand the NEXT dmp2_fold / dmp2_fold_host call of this engine the vgru state of its alignment
+ * ([L][512] fp32 on the device, what dmp2_vgru returns) instead of letting it scan the MSA.  The scan (network.py:223-224)
+ * is independent per alignment column and latency-bound (N dependent steps that each occupy ~all SMs mostly waiting), so a
+ * scheduler folding several alignments with the same N calls dmp2_vgru ONCE on their columns side by side
+ * ([N][L1 + L2 + ...]) and gives every fold its slice -- bit-identical to the fold's own scan.  One-shot: cleared by the
+ * fold that consumes it; the buffer must stay valid until that fold has finished on its stream.  NULL cancels. */
+int dmp2_set_vgru_input(dmp2_engine* e, const float* vgru_dev);
+
+/* Tuning: dynamic unit schedule of the persistent conv kernel (on != 0).  The CTA clusters claim their work units from a
+ * device counter instead of the static round-robin, so a conv launch that finds part of the SMs occupied by the kernels
+ * of another stream is finished by the CTAs that did start.  Meant for several folds in flight on one GPU
+ * (parallel.StreamPool turns it on); the conv output is bit-identical, the fused InstanceNorm sums are fp64 sums formed
+ * in a run-dependent order (differences at the 1e-16 level before rounding to fp32). */
+int dmp2_set_conv_dynamic(dmp2_engine* e, int on);
+
 #ifdef __cplusplus
 }
 #endif

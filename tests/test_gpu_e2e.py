@@ -180,6 +180,52 @@ def test_batch_api(pf10963, tmp_path):
 
 
 @needs_weights
+def test_shared_vgru_scan_is_bit_identical(state_dict, pf10963):
+    """Throughput mode scans the alignment columns of several targets in ONE vgru call (the scan is independent per
+    column) and hands every fold its slice (dmp2_set_vgru_input).  The slice must be bit-identical to the fold's own
+    scan and so must the fold; the hand-over is one-shot (the next fold scans again)."""
+    from dmpfold2_b200.engine import Engine
+    from dmpfold2_b200.parallel import StreamPool
+    from dmpfold2_b200.synth import synth_msa_structured
+    msas = [torch.from_numpy(synth_msa_structured(pf10963, l, 48, 30 + l)).cuda() for l in (82, 150, 100, 64, 130)]
+    e, scan = Engine(state_dict, 0), Engine(state_dict, 0)
+    try:
+        want = [e.fold(m, None, 1, 10) for m in msas]
+        state = scan.vgru(torch.cat(msas[:3], dim=1).contiguous())
+        assert torch.equal(state[82:232], e.vgru(msas[1]))
+        c, f = e.fold(msas[1], None, 1, 10, vgru=state[82:232])
+        assert torch.equal(c, want[1][0]) and torch.equal(f, want[1][1])
+        c, f = e.fold(msas[3], None, 1, 10)                    # one-shot: this fold scans its own alignment
+        assert torch.equal(c, want[3][0])
+        with pytest.raises(ValueError):
+            e.fold(msas[1], None, 1, 10, vgru=state[:100])
+    finally:
+        e.close()
+        scan.close()
+    # the pool: 5 targets on 2 streams, scans shared by (82+150+100), (64+130); static conv schedule -> same bits
+    pool = StreamPool(state_dict, 0, streams=2, conv_dynamic=False, scan_rows=384)
+    try:
+        from dmpfold2_b200.parallel import scan_batches
+        assert scan_batches([(48, int(m.shape[1])) for m in msas], 384) == [[0, 1, 2], [3, 4]]
+        for threads in (True, False):
+            got = pool.fold_all(msas, None, 1, 10, host_threads=threads)
+            torch.cuda.synchronize()
+            for (c, f), (wc, wf) in zip(got, want):
+                assert torch.equal(c, wc) and torch.equal(f, wf)
+    finally:
+        pool.close()
+    # default pool (dynamic conv schedule: InstanceNorm sums in a run-dependent fp64 order): same result to rounding
+    pool = StreamPool(state_dict, 0, streams=3)
+    try:
+        got = pool.fold_all(msas, None, 1, 10)
+        torch.cuda.synchronize()
+        for (c, f), (wc, wf) in zip(got, want):
+            assert O.kabsch_rmsd(c[:, 1].cpu().numpy(), wc[:, 1].cpu().numpy()) < 1e-5
+    finally:
+        pool.close()
+
+
+@needs_weights
 def test_fused_stats_variant(state_dict, pf10963, monkeypatch):
     """DMP2_FUSE_STATS=0: the InstanceNorm sums come from a separate k_in_stats pass instead of the conv epilogue (the
     default).  Same statistics up to the summation order, so the two folds must agree far below the parity tolerance."""

@@ -270,6 +270,40 @@ def test_vgru_long_wavefront(eng, oracle, pf10963):
     assert (one - oracle.vgru_last(torch.from_numpy(msa[:1]))).abs().max() < 1e-5
 
 
+@pytest.mark.parametrize('cluster,sms', [('pair', '0'), ('pair', '6'), ('1', '3'), ('2', '20')])
+def test_conv_dynamic_schedule_is_bit_identical(state_dict, oracle, pf10963, cluster, sms, monkeypatch):
+    """Throughput mode's dynamic unit schedule (the clusters claim units from a device counter; dmp2_set_conv_dynamic):
+    every unit is computed exactly as in the static schedule whichever cluster runs it, so the conv output must be
+    BIT-identical, launch after launch (the counter is never reset: every launch owns the next range of values);
+    the fused InstanceNorm sums (fp64, run-dependent order) must give the same block output to fp32 rounding."""
+    from dmpfold2_b200.engine import Engine
+    monkeypatch.setenv('DMP2_CONV_CLUSTER', cluster)
+    monkeypatch.setenv('DMP2_CONV_SMS', sms)
+    es, ed = Engine(state_dict, 0), Engine(state_dict, 0)
+    ed.set_conv_dynamic(True)
+    try:
+        g = torch.Generator().manual_seed(78)
+        for l in (19, 82, 150):
+            x = _nhwc(torch.randn(1, 128, l, l, generator=g) * 3)
+            for mode in ('f16x3', 'f16f8', 'f16'):
+                es.set_conv_mode(mode)
+                ed.set_conv_mode(mode)
+                want = es.conv5_maxout(5, x)
+                for rep in range(3):
+                    assert torch.equal(ed.conv5_maxout(5, x), want), (cluster, sms, mode, l, rep)
+                if mode != 'f16':
+                    a, b = es.resblock(5, x), ed.resblock(5, x)
+                    assert _rel(b.cpu(), a.cpu()) < 1e-6, (cluster, sms, mode, l)
+        if cluster == 'pair' and sms == '0':                 # and a whole fold
+            msa = O.synth_msa_structured(pf10963, 120, 64, 5)
+            c0, f0 = es.fold_host(msa, None, 2, 20)
+            c1, f1 = ed.fold_host(msa, None, 2, 20)
+            assert O.kabsch_rmsd(c0[:, 1], c1[:, 1]) < 1e-5 and np.abs(f0 - f1).max() < 1e-5
+    finally:
+        es.close()
+        ed.close()
+
+
 @pytest.mark.parametrize('cluster,sms', [('1', '0'), ('2', '20'), ('1', '3')])
 def test_conv_cluster_variants(state_dict, oracle, cluster, sms, monkeypatch):
     """The persistent conv kernel without weight multicast (cluster of 1), and on a restricted number of SMs (every

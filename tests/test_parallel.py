@@ -151,3 +151,15 @@ def test_two_rank_gloo_strip_group_host_logic(tmp_path):
     port = _free_port()
     mp.spawn(_strip_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert sorted(os.listdir(tmp_path)) == ['strip_ok0', 'strip_ok1']
+
+
+def test_scan_batches_groups_consecutive_targets_with_equal_depth():
+    """StreamPool's shared vgru scans: consecutive targets with the same N whose columns fit `scan_rows` together."""
+    from dmpfold2_b200.parallel import scan_batches
+    assert scan_batches([(512, 150)] * 5, 384) == [[0, 1], [2, 3]]                  # the odd one scans alone
+    assert scan_batches([(512, 150)] * 5, 768) == [[0, 1, 2, 3, 4]]
+    assert scan_batches([(1000, 300), (1000, 300)], 384) == []                        # one target already fills a wave
+    assert scan_batches([(1000, 300), (1000, 300), (1000, 300)], 600) == [[0, 1]]
+    assert scan_batches([(10, 82), (11, 82), (11, 40), (11, 500), (11, 60), (11, 70)], 384) == [[1, 2], [4, 5]]
+    assert scan_batches([], 384) == [] and scan_batches([(5, 50)], 384) == []
+    assert scan_batches([(5, 128), (5, 128), (5, 128), (5, 128)], 384) == [[0, 1, 2]]
