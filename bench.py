@@ -280,11 +280,11 @@ def main():
 
     # ---- informational: throughput mode (dmpfold2_b200.parallel.StreamPool): K engines on K streams of this GPU fold
     # independent targets concurrently (the one-target-per-stream layout of BASELINE.json configs[2]); the latency-bound
-    # stages of one target overlap the convs of the others.  conv_sms < 148 leaves SMs to those small kernels.
+    # stages of one target overlap the convs of the others (profiles/round2_throughput_v2.txt has the full sweep).
     tp_ms = {}
     try:
         from dmpfold2_b200.parallel import StreamPool
-        for k_streams, conv_sms in (() if args.no_extras else ((2, 0), (3, 0), (3, 132))):
+        for k_streams, conv_sms in (() if args.no_extras else ((2, 0), (3, 0))):
             pool = StreamPool(sd, local_rank, streams=k_streams, conv_mode=args.conv_mode, conv_sms=conv_sms)
             n_tp = max(k_streams * 2, (args.steps // k_streams) * k_streams)
             idx = [args.warmup + (k % args.steps) for k in range(n_tp)]

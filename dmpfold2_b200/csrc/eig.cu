@@ -6,7 +6,8 @@
 //      per column through distributed shared memory (st.async + mbarrier, no cluster barrier in the loop);
 //      beyond the cluster's capacity the same fused scheme runs on the whole GPU (k_tridiag_grid);
 //   2. Sturm multi-section (32 shifts per round) for the 8 largest eigenvalues      } CTA 0
-//   3. inverse iteration + Gram-Schmidt, 4. back-transformation                      }
+//   3. inverse iteration + Gram-Schmidt                                              }
+//   4. back-transformation z <- H_0 ... H_{n-3} z: ONE CTA PER EIGENVECTOR (CTA w of the cluster takes vector w)
 //   5. canonical sign (largest-|component| positive, lowest index wins ties), sqrt(clamp(relu(l),1e-8)) scaling.
 #include "common.cuh"
 #include <stdlib.h>
@@ -114,9 +115,7 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
     // pre_tridiag: d, e, beta and V were produced by k_tridiag_grid; only CTA 0 has work left (no cluster barrier is
     // executed by anybody on this path)
     __shared__ double scr_a[EIG_THREADS / 32], scr_b[EIG_THREADS / 32];
-    if (pre_tridiag) {
-        if (c != 0) return;
-    } else {
+    if (!pre_tridiag) {
     stamp(0);
     const int nloc = (n - c + EIG_CL - 1) / EIG_CL;
     double* rbase;
@@ -245,9 +244,11 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
     }
     __threadfence();
     cluster.sync();
-    if (c != 0) return;                                // phases 2-5 only touch global memory and CTA 0's smem
     stamp(1);
     }
+    // phases 2-3: CTA 0 (the others wait at the cluster barrier below); phases 4-5: CTA w < 8 takes eigenvector w
+    double* lam_g = wk + 35 * n + 8;                   // [8] eigenvalues, handed from CTA 0 to the others (stamps sit at 35 n)
+    if (c == 0) {
 
     for (int i = tid; i < n; i += EIG_THREADS) { sd[i] = gd[i]; se[i] = ge[i]; se2[i] = ge[i] * ge[i]; }
     __syncthreads();
@@ -386,62 +387,60 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
     }
 
     stamp(3);
-    // ---------------- 4. back-transform: z <- H_0 H_1 ... H_{n-3} z  (warp w owns vector w) --------------
-    // Reflectors are staged `stage_rows` at a time into shared memory by all warps (one L2 round trip per block
-    // instead of one per reflector) when the eigenvectors live in shared memory; otherwise they are read in place.
-    if (vec_in_smem) {
-        double* stage = vec_in_smem == 1 ? u0 : big + 8 * n;      // mode 1: the 24 n doubles of the LU factors are free now
-        for (int khi = n - 3; khi >= 0; khi -= stage_rows) {
-            const int klo = khi - (stage_rows - 1) > 0 ? khi - (stage_rows - 1) : 0;
-            // all threads share the block of reflectors evenly, so the loads of one stage are one round of L2 latency
+    // hand the eigenvectors of T (and the eigenvalues) to the other CTAs through global memory
+    if (vec_in_smem) for (int i = tid; i < 8 * n; i += EIG_THREADS) gvec[i] = zs[i];
+    if (tid < 8) lam_g[tid] = lam[tid];
+    __threadfence();
+    }
+    cluster.sync();
+    if (c >= 8) return;
+    // ---------------- 4. back-transform: z <- H_0 H_1 ... H_{n-3} z, ONE CTA PER EIGENVECTOR ---------------
+    // The eight vectors are independent, and so far seven (or fifteen) CTAs of the cluster had nothing left to do.  CTA w
+    // keeps vector w in shared memory, thread t owning the rows j = t (mod EIG_THREADS) for the whole phase (no
+    // cross-thread hazard on z); the reflectors are staged `srows` at a time into shared memory by all threads (one L2
+    // round trip per block); per reflector: partial dot, warp shuffle, ONE block barrier, total, update.
+    {
+        const int w = c;
+        double* z = sm;                                         // [n]
+        double* stage = sm + n;                                 // [srows][n]
+        __shared__ double part[2][EIG_THREADS / 32];
+        __shared__ double sbeta[64];
+        const int srows = stage_rows;
+        for (int i = tid; i < n; i += EIG_THREADS) z[i] = __ldcg(gvec + (int64_t)w * n + i);
+        const double lamw = __ldcg(lam_g + w);
+        int pp = 0;
+        for (int khi = n - 3; khi >= 0; khi -= srows) {
+            const int klo = khi - (srows - 1) > 0 ? khi - (srows - 1) : 0;
+            __syncthreads();                                    // the previous block of reflectors is no longer read
             const int tot = (khi - klo + 1) * n;
 #pragma unroll 4
             for (int idx = tid; idx < tot; idx += EIG_THREADS) {
                 const int r = idx / n, i = idx - r * n;
                 if (i < n - (klo + r) - 1) stage[idx] = __ldcg(V + (int64_t)(klo + r) * n + i);
             }
+            if (tid <= khi - klo) sbeta[tid] = beta[klo + tid];
             __syncthreads();
-            if (warp < 8) {
-                double* z = zs + warp * n;
-                for (int k = khi; k >= klo; k--) {
-                    const double bt = beta[k];
-                    if (bt == 0.0) continue;
-                    const int m = n - k - 1;
-                    const double* v = stage + (k - klo) * n;
-                    double* zz = z + k + 1;
-                    double a = 0.0, a2 = 0.0;
-                    int i = lane;
-#pragma unroll 2
-                    for (; i + 32 < m; i += 64) { a += v[i] * zz[i]; a2 += v[i + 32] * zz[i + 32]; }
-                    if (i < m) a += v[i] * zz[i];
-                    a = warp_sum(a + a2) * bt;
-#pragma unroll 4
-                    for (i = lane; i < m; i += 32) zz[i] -= a * v[i];
-                    __syncwarp();
-                }
+            for (int k = khi; k >= klo; k--) {
+                const double bt = sbeta[k - klo];
+                if (bt == 0.0) continue;                        // (uniform)
+                const double* v = stage + (k - klo) * n - (k + 1);        // v[j] = component of row j
+                double a = 0.0;
+                for (int j = tid; j < n; j += EIG_THREADS) if (j > k) a += v[j] * z[j];
+                a = warp_sum(a);
+                if (lane == 0) part[pp][warp] = a;
+                __syncthreads();
+                double t = 0.0;
+#pragma unroll
+                for (int i = 0; i < EIG_THREADS / 32; i++) t += part[pp][i];
+                t *= bt;
+                for (int j = tid; j < n; j += EIG_THREADS) if (j > k) z[j] -= t * v[j];
+                pp ^= 1;
             }
-            __syncthreads();
         }
-    } else if (warp < 8) {
-        double* z = zs + warp * n;
-        for (int k = n - 3; k >= 0; k--) {
-            const double bt = beta[k];
-            if (bt == 0.0) continue;
-            const int m = n - k - 1;
-            const double* v = V + (int64_t)k * n;
-            double* zz = z + k + 1;
-            double a = 0.0;
-            for (int i = lane; i < m; i += 32) a += v[i] * zz[i];
-            a = warp_sum(a) * bt;
-            for (int i = lane; i < m; i += 32) zz[i] -= a * v[i];
-            __syncwarp();
-        }
-    }
-    if (warp < 8) {
-        double* z = zs + warp * n;
+        __syncthreads();
         // ---------------- 5. canonical sign + MDS scaling -------------------------------------------------
         double best = -1.0; int bi = 0;
-        for (int i = lane; i < n; i += 32) {
+        for (int i = tid; i < n; i += EIG_THREADS) {
             double a = fabs((double)(float)z[i]);
             if (a > best) { best = a; bi = i; }
         }
@@ -450,15 +449,23 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
             int oi = __shfl_xor_sync(0xffffffffu, bi, o);
             if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
         }
-        const double sgn = z[bi] < 0.0 ? -1.0 : 1.0;
-        const float lf = (float)lam[warp];
-        const float sc = sqrtf(fmaxf(fmaxf(lf, 0.0f), 1e-8f));
-        for (int i = lane; i < n; i += 32) {
-            float vf = (float)(z[i] * sgn);
-            if (vec_out) vec_out[(int64_t)i * 8 + warp] = vf;
-            if (mds_out) mds_out[(int64_t)i * 8 + warp] = vf * sc;
+        __shared__ double wbest[EIG_THREADS / 32];
+        __shared__ int wbi[EIG_THREADS / 32];
+        if (lane == 0) { wbest[warp] = best; wbi[warp] = bi; }
+        __syncthreads();
+        for (int i = 0; i < EIG_THREADS / 32; i++) {
+            const double ob = wbest[i]; const int oi = wbi[i];
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
         }
-        if (lane == 0 && vals_out) vals_out[warp] = lf;
+        const double sgn = z[bi] < 0.0 ? -1.0 : 1.0;
+        const float lf = (float)lamw;
+        const float sc = sqrtf(fmaxf(fmaxf(lf, 0.0f), 1e-8f));
+        for (int i = tid; i < n; i += EIG_THREADS) {
+            float vf = (float)(z[i] * sgn);
+            if (vec_out) vec_out[(int64_t)i * 8 + w] = vf;
+            if (mds_out) mds_out[(int64_t)i * 8 + w] = vf * sc;
+        }
+        if (tid == 0 && vals_out) vals_out[w] = lf;
     }
     __syncthreads();
     stamp(4);
@@ -625,6 +632,9 @@ template <int CL>
 static int launch_eig(dmp2_engine* e, const float* m, int L, int rows_in_smem, int vec_in_smem, int pre_tridiag, size_t smem,
                       float* vals, float* mds_scaled, float* vecs_raw, cudaStream_t st, int stage_rows = 16) {
     double* V = e->ws.eig_a + (int64_t)L * L;
+    // phase 4 keeps one eigenvector (L doubles) + a block of reflectors in every CTA's shared memory
+    stage_rows = (int)std::min<size_t>(64, (smem / 8 - (size_t)L) / (size_t)L);
+    if (stage_rows < 1) return e->fail(DMP2_ERR_UNSUPPORTED, "eig_top8: L too large");
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(CL);
     cfg.blockDim = dim3(EIG_THREADS);
@@ -694,12 +704,12 @@ int run_eig_top8(dmp2_engine* e, const float* m, int L, float* vals, float* mds_
         POST_LAUNCH(e, "k_tridiag_grid");
         // phases 2-5 in CTA 0: d, e, e^2 (3 n) + as much of the work vectors as fits
         const size_t cap = LIMIT / 8;
-        int vmode = 0, srows = 16;
+        int vmode = 0;
         size_t words = 3 * n;
         if (35 * n <= cap) { vmode = 1; words = 35 * n; }
-        else if (13 * n <= cap) { vmode = 2; srows = (int)std::min<size_t>(16, (cap - 11 * n) / n); words = (11 + srows) * n; }
+        else if (11 * n <= cap) { vmode = 2; words = 11 * n; }
         if (words > cap) return e->fail(DMP2_ERR_UNSUPPORTED, "eig_top8: L too large");
-        return launch_eig<8>(e, m, L, 0, vmode, 1, words * 8, vals, mds_scaled, vecs_raw, st, srows);
+        return launch_eig<8>(e, m, L, 0, vmode, 1, LIMIT, vals, mds_scaled, vecs_raw, st);     // all of it: phase 4 stages reflectors
     }
     if (s16 > LIMIT) return e->fail(DMP2_ERR_UNSUPPORTED, "eig_top8: L too large");
     if (!e->eig_no_cl16) {
