@@ -403,7 +403,8 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
         const int w = c;
         double* z = sm;                                         // [n]
         double* stage = sm + n;                                 // [srows][n]
-        __shared__ double part[2][EIG_THREADS / 32];
+        __shared__ __align__(16) double part[2][EIG_THREADS / 32];
+        static_assert(EIG_THREADS == 512, "the partial-sum tree below is written for 16 warps");
         __shared__ double sbeta[64];
         const int srows = stage_rows;
         for (int i = tid; i < n; i += EIG_THREADS) z[i] = __ldcg(gvec + (int64_t)w * n + i);
@@ -429,9 +430,13 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
                 a = warp_sum(a);
                 if (lane == 0) part[pp][warp] = a;
                 __syncthreads();
-                double t = 0.0;
-#pragma unroll
-                for (int i = 0; i < EIG_THREADS / 32; i++) t += part[pp][i];
+                double t;
+                {   // fixed-order pairwise tree over the 16 warp partials (depth 4 instead of a chain of 16 dependent adds)
+                    const double2* pq = reinterpret_cast<const double2*>(part[pp]);
+                    const double2 q0 = pq[0], q1 = pq[1], q2 = pq[2], q3 = pq[3], q4 = pq[4], q5 = pq[5], q6 = pq[6], q7 = pq[7];
+                    t = (((q0.x + q0.y) + (q1.x + q1.y)) + ((q2.x + q2.y) + (q3.x + q3.y))) +
+                        (((q4.x + q4.y) + (q5.x + q5.y)) + ((q6.x + q6.y) + (q7.x + q7.y)));
+                }
                 t *= bt;
                 for (int j = tid; j < n; j += EIG_THREADS) if (j > k) z[j] -= t * v[j];
                 pp ^= 1;
