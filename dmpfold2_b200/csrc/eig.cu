@@ -77,6 +77,14 @@ __device__ __forceinline__ double block_sum1(double v, double* scr) {
     return t;
 }
 
+// fixed-order pairwise sum of 16 doubles in shared memory (depth 4 instead of a chain of 16 dependent adds)
+__device__ __forceinline__ double tree16(const double* p) {
+    const double2* pq = reinterpret_cast<const double2*>(p);
+    const double2 q0 = pq[0], q1 = pq[1], q2 = pq[2], q3 = pq[3], q4 = pq[4], q5 = pq[5], q6 = pq[6], q7 = pq[7];
+    return (((q0.x + q0.y) + (q1.x + q1.y)) + ((q2.x + q2.y) + (q3.x + q3.y))) +
+           (((q4.x + q4.y) + (q5.x + q5.y)) + ((q6.x + q6.y) + (q7.x + q7.y)));
+}
+
 // rows_smem: doubles of shared memory reserved for the matrix rows (0 = rows stay in global memory A)
 // vec_smem:  1 = the inverse-iteration work vectors (32 n doubles) live in shared memory
 // inverse-iteration sweeps per eigenvector (DMP2_EIG_INVIT overrides; the shifts come out of the Sturm multi-section
@@ -246,10 +254,10 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
     cluster.sync();
     stamp(1);
     }
-    // phases 2-3: CTA 0 (the others wait at the cluster barrier below); phases 4-5: CTA w < 8 takes eigenvector w
-    double* lam_g = wk + 35 * n + 8;                   // [8] eigenvalues, handed from CTA 0 to the others (stamps sit at 35 n)
-    if (c == 0) {
-
+    // phase 2 and phases 4-5: CTA w < 8 takes eigenvalue / eigenvector w; phase 3: CTA 0 (the others wait at a cluster barrier)
+    double* lam_g = wk + 35 * n + 8;                   // [8] eigenvalues, exchanged through global memory (stamps sit at 35 n)
+    double tnorm = 0.0;
+    if (c < 8) {
     for (int i = tid; i < n; i += EIG_THREADS) { sd[i] = gd[i]; se[i] = ge[i]; se2[i] = ge[i] * ge[i]; }
     __syncthreads();
     // Gershgorin bounds
@@ -268,30 +276,40 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
     __syncthreads();
     double gl = glo[0], gh = ghi[0];
     for (int i = 1; i < NW; i++) { gl = fmin(gl, glo[i]); gh = fmax(gh, ghi[i]); }
-    const double tnorm = fmax(fabs(gl), fabs(gh));
+    tnorm = fmax(fabs(gl), fabs(gh));
     gl -= tnorm * 1e-12 + 1e-300;
     gh += tnorm * 1e-12 + 1e-300;
 
-    // ---------------- 2. Sturm multi-section: warp w finds eigenvalue index n-8+w (ascending) -----------
-    if (warp < 8) {
-        const int kidx = n - 8 + warp;
+    // ---------------- 2. Sturm multi-section: CTA w finds eigenvalue index n-8+w (ascending) --------------
+    // 512 shifts per round, one per thread (each a serial n-step Sturm recurrence): the bracket shrinks 513x per
+    // round, 6 rounds from the Gershgorin interval to 4 ulp (33 shifts per round in one warp needed 10-11).
+    {
+        const int kidx = n - 8 + c;
+        __shared__ int wcnt[2][NW];
         double lo = gl, hi = gh;
-        for (int round = 0; round < 16; round++) {
-            double step = (hi - lo) / 33.0;
-            double x = lo + step * (double)(lane + 1);
-            int cnt = sturm_count(sd, se2, n, x);
-            unsigned bal = __ballot_sync(0xffffffffu, cnt <= kidx);
-            int npre = __popc(bal);
-            double x_lo = __shfl_sync(0xffffffffu, x, npre > 0 ? npre - 1 : 0);
-            double x_hi = __shfl_sync(0xffffffffu, x, npre < 32 ? npre : 31);
-            double nlo = npre > 0 ? x_lo : lo;
-            double nhi = npre < 32 ? x_hi : hi;
-            bool done = !(nhi - nlo < hi - lo) || (nhi - nlo) <= 4.0 * 2.3e-16 * fmax(fabs(nlo), fabs(nhi));
+        for (int round = 0; round < 12; round++) {
+            const double step = (hi - lo) / (double)(EIG_THREADS + 1);
+            const double x = lo + step * (double)(tid + 1);
+            const int cnt = sturm_count(sd, se2, n, x);
+            const unsigned bal = __ballot_sync(0xffffffffu, cnt <= kidx);
+            if (lane == 0) wcnt[round & 1][warp] = __popc(bal);
+            __syncthreads();
+            int npre = 0;                                       // shifts with at most kidx eigenvalues below them (a prefix)
+#pragma unroll
+            for (int i = 0; i < NW; i++) npre += wcnt[round & 1][i];
+            const double nlo = npre > 0 ? lo + step * (double)npre : lo;
+            const double nhi = npre < EIG_THREADS ? lo + step * (double)(npre + 1) : hi;
+            const bool done = !(nhi - nlo < hi - lo) || (nhi - nlo) <= 4.0 * 2.3e-16 * fmax(fabs(nlo), fabs(nhi));
             lo = nlo; hi = nhi;
-            if (done) break;
+            if (done) break;                                    // (uniform: every thread holds the same bracket)
         }
-        if (lane == 0) lam[warp] = 0.5 * (lo + hi);
+        if (tid == 0) lam_g[c] = 0.5 * (lo + hi);
     }
+    __threadfence();
+    }
+    cluster.sync();
+    if (c == 0) {
+    if (tid < 8) lam[tid] = __ldcg(lam_g + tid);
     __syncthreads();
 
     stamp(2);
@@ -389,7 +407,6 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
     stamp(3);
     // hand the eigenvectors of T (and the eigenvalues) to the other CTAs through global memory
     if (vec_in_smem) for (int i = tid; i < 8 * n; i += EIG_THREADS) gvec[i] = zs[i];
-    if (tid < 8) lam_g[tid] = lam[tid];
     __threadfence();
     }
     cluster.sync();
@@ -403,7 +420,7 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
         const int w = c;
         double* z = sm;                                         // [n]
         double* stage = sm + n;                                 // [srows][n]
-        __shared__ __align__(16) double part[2][EIG_THREADS / 32];
+        __shared__ __align__(16) double part[2][3][EIG_THREADS / 32];
         static_assert(EIG_THREADS == 512, "the partial-sum tree below is written for 16 warps");
         __shared__ double sbeta[64];
         const int srows = stage_rows;
@@ -421,23 +438,38 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
             }
             if (tid <= khi - klo) sbeta[tid] = beta[klo + tid];
             __syncthreads();
-            for (int k = khi; k >= klo; k--) {
+            int k = khi;
+            for (; k - 1 >= klo; k -= 2) {
+                // reflectors k (applied first) and k-1 in ONE barrier round: with p = v_k.z, q = v_{k-1}.z, r = v_{k-1}.v_k
+                //   a_k = beta_k p,   a_{k-1} = beta_{k-1} (q - a_k r),   z -= a_k v_k + a_{k-1} v_{k-1}
+                const double bk = sbeta[k - klo], bm = sbeta[k - 1 - klo];
+                const double* vk = stage + (k - klo) * n - (k + 1);         // vk[j]: component of row j (rows j > k)
+                const double* vm = stage + (k - 1 - klo) * n - k;           // vm[j]: rows j > k-1
+                double pa = 0.0, qa = 0.0, ra = 0.0;
+                for (int j = tid; j < n; j += EIG_THREADS) {
+                    if (j > k) { const double a = vk[j], b = vm[j], zz = z[j]; pa += a * zz; qa += b * zz; ra += a * b; }
+                    else if (j == k) qa += vm[j] * z[j];
+                }
+                pa = warp_sum(pa); qa = warp_sum(qa); ra = warp_sum(ra);
+                if (lane == 0) { part[pp][0][warp] = pa; part[pp][1][warp] = qa; part[pp][2][warp] = ra; }
+                __syncthreads();
+                const double ak = bk * tree16(part[pp][0]);
+                const double am = bm * (tree16(part[pp][1]) - ak * tree16(part[pp][2]));
+                for (int j = tid; j < n; j += EIG_THREADS) {
+                    if (j > k) z[j] -= ak * vk[j] + am * vm[j];
+                    else if (j == k) z[j] -= am * vm[j];
+                }
+                pp ^= 1;
+            }
+            if (k >= klo) {                                     // odd one left in this block
                 const double bt = sbeta[k - klo];
-                if (bt == 0.0) continue;                        // (uniform)
-                const double* v = stage + (k - klo) * n - (k + 1);        // v[j] = component of row j
+                const double* v = stage + (k - klo) * n - (k + 1);
                 double a = 0.0;
                 for (int j = tid; j < n; j += EIG_THREADS) if (j > k) a += v[j] * z[j];
                 a = warp_sum(a);
-                if (lane == 0) part[pp][warp] = a;
+                if (lane == 0) part[pp][0][warp] = a;
                 __syncthreads();
-                double t;
-                {   // fixed-order pairwise tree over the 16 warp partials (depth 4 instead of a chain of 16 dependent adds)
-                    const double2* pq = reinterpret_cast<const double2*>(part[pp]);
-                    const double2 q0 = pq[0], q1 = pq[1], q2 = pq[2], q3 = pq[3], q4 = pq[4], q5 = pq[5], q6 = pq[6], q7 = pq[7];
-                    t = (((q0.x + q0.y) + (q1.x + q1.y)) + ((q2.x + q2.y) + (q3.x + q3.y))) +
-                        (((q4.x + q4.y) + (q5.x + q5.y)) + ((q6.x + q6.y) + (q7.x + q7.y)));
-                }
-                t *= bt;
+                const double t = bt * tree16(part[pp][0]);
                 for (int j = tid; j < n; j += EIG_THREADS) if (j > k) z[j] -= t * v[j];
                 pp ^= 1;
             }
