@@ -45,22 +45,34 @@ __device__ __forceinline__ int sturm_count(const double* d, const double* e2, in
     if (p == 0.0) p = -1e-300;
     int sp = (unsigned)__double2hiint(p) >> 31;
     int cnt = sp;
-    int i = 1;
-    while (i < n) {
-        const int iend = min(n, i + 8);
-#pragma unroll 8
-        for (; i < iend; i++) {
-            double pn = fma(d[i] - x, p, -(e2[i - 1] * pm));
-            const int hi = __double2hiint(pn), lo = __double2loint(pn);
-            if (((hi << 1) | lo) == 0) pn = sp ? 1e-300 : -1e-300;       // exact zero: opposite sign of its predecessor
-            const int sn = (unsigned)__double2hiint(pn) >> 31;
-            cnt += sn ^ sp;
-            sp = sn;
-            pm = p; p = pn;
-        }
+    auto step = [&](double dx, double ee) {
+        double pn = fma(dx, p, -(ee * pm));
+        const int hi = __double2hiint(pn), lo = __double2loint(pn);
+        if (((hi << 1) | lo) == 0) pn = sp ? 1e-300 : -1e-300;           // exact zero: opposite sign of its predecessor
+        const int sn = (unsigned)__double2hiint(pn) >> 31;
+        cnt += sn ^ sp;
+        sp = sn;
+        pm = p; p = pn;
+    };
+    auto rescale = [&]() {
         const int ex = (__double2hiint(p) >> 20) & 0x7ff;
         if (ex > 1023 + 400) { p *= 3.8725919148493183e-121; pm *= 3.8725919148493183e-121; }        // 2^-400
         else if (ex < 1023 - 400) { p *= 2.5822498780869086e120; pm *= 2.5822498780869086e120; }      // 2^400
+    };
+    int i = 1;
+    // blocks of 8 rows: all operands of the block are fetched (and d - x formed) BEFORE the dependent chain starts, so a
+    // row costs one DFMA + the zero test instead of a shared-memory round trip per row (which tripled the chain)
+    for (; i + 8 <= n; i += 8) {
+        double dx[8], ee[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) { dx[u] = d[i + u] - x; ee[u] = e2[i + u - 1]; }
+#pragma unroll
+        for (int u = 0; u < 8; u++) step(dx[u], ee[u]);
+        rescale();
+    }
+    if (i < n) {
+        for (; i < n; i++) step(d[i] - x, e2[i - 1]);
+        rescale();
     }
     return cnt;
 }
@@ -68,12 +80,13 @@ __device__ __forceinline__ int sturm_count(const double* d, const double* e2, in
 // one-barrier block reduction: every thread returns the same total (fixed order); `scr` holds EIG_THREADS/32 doubles
 // and must not be reused before another block-wide barrier has been passed
 __device__ __forceinline__ double block_sum1(double v, double* scr) {
+    static_assert(EIG_THREADS == 512, "16 warp partials: one per lane of a half warp");
     v = warp_sum(v);
     if ((threadIdx.x & 31) == 0) scr[threadIdx.x >> 5] = v;
     __syncthreads();
-    double t = 0.0;
+    double t = scr[threadIdx.x & 15];              // lane-parallel pairwise tree: 4 adds per warp instead of a chain of 16
 #pragma unroll
-    for (int i = 0; i < EIG_THREADS / 32; i++) t += scr[i];
+    for (int o = 8; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
     return t;
 }
 
@@ -83,6 +96,16 @@ __device__ __forceinline__ double tree16(const double* p) {
     const double2 q0 = pq[0], q1 = pq[1], q2 = pq[2], q3 = pq[3], q4 = pq[4], q5 = pq[5], q6 = pq[6], q7 = pq[7];
     return (((q0.x + q0.y) + (q1.x + q1.y)) + ((q2.x + q2.y) + (q3.x + q3.y))) +
            (((q4.x + q4.y) + (q5.x + q5.y)) + ((q6.x + q6.y) + (q7.x + q7.y)));
+}
+
+// two warp reductions for the price of one and a bit: lanes < 16 return the warp's sum of p, lanes >= 16 that of q
+__device__ __forceinline__ double warp_sum_pair(double p, double q, int lane) {
+    const bool up = (lane & 16) != 0;
+    double keep = up ? q : p;
+    keep += __shfl_xor_sync(0xffffffffu, up ? p : q, 16);
+#pragma unroll
+    for (int o = 8; o; o >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
+    return keep;
 }
 
 // rows_smem: doubles of shared memory reserved for the matrix rows (0 = rows stay in global memory A)
@@ -281,24 +304,29 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
     gh += tnorm * 1e-12 + 1e-300;
 
     // ---------------- 2. Sturm multi-section: CTA w finds eigenvalue index n-8+w (ascending) --------------
-    // 512 shifts per round, one per thread (each a serial n-step Sturm recurrence): the bracket shrinks 513x per
-    // round, 6 rounds from the Gershgorin interval to 4 ulp (33 shifts per round in one warp needed 10-11).
+    // 128 shifts per round, one per thread of the first four warps (one warp per SM sub-partition; each shift is a serial
+    // n-step Sturm recurrence and the fp64 pipe is what bounds it: measured 7 us per round and warp-per-partition at
+    // n=300).  The bracket shrinks 129x per round: 8 rounds from the Gershgorin interval to 4 ulp, where 33 shifts in
+    // one warp needed 11 and 513 shifts in sixteen warps 7 rounds of four times the work.
     {
+        constexpr int NSH = 128;
         const int kidx = n - 8 + c;
-        __shared__ int wcnt[2][NW];
+        __shared__ int wcnt[2][NSH / 32];
         double lo = gl, hi = gh;
-        for (int round = 0; round < 12; round++) {
-            const double step = (hi - lo) / (double)(EIG_THREADS + 1);
-            const double x = lo + step * (double)(tid + 1);
-            const int cnt = sturm_count(sd, se2, n, x);
-            const unsigned bal = __ballot_sync(0xffffffffu, cnt <= kidx);
-            if (lane == 0) wcnt[round & 1][warp] = __popc(bal);
+        for (int round = 0; round < 16; round++) {
+            const double step = (hi - lo) / (double)(NSH + 1);
+            if (tid < NSH) {
+                const double x = lo + step * (double)(tid + 1);
+                const int cnt = sturm_count(sd, se2, n, x);
+                const unsigned bal = __ballot_sync(0xffffffffu, cnt <= kidx);
+                if (lane == 0) wcnt[round & 1][warp] = __popc(bal);
+            }
             __syncthreads();
             int npre = 0;                                       // shifts with at most kidx eigenvalues below them (a prefix)
 #pragma unroll
-            for (int i = 0; i < NW; i++) npre += wcnt[round & 1][i];
+            for (int i = 0; i < NSH / 32; i++) npre += wcnt[round & 1][i];
             const double nlo = npre > 0 ? lo + step * (double)npre : lo;
-            const double nhi = npre < EIG_THREADS ? lo + step * (double)(npre + 1) : hi;
+            const double nhi = npre < NSH ? lo + step * (double)(npre + 1) : hi;
             const bool done = !(nhi - nlo < hi - lo) || (nhi - nlo) <= 4.0 * 2.3e-16 * fmax(fabs(nlo), fabs(nhi));
             lo = nlo; hi = nhi;
             if (done) break;                                    // (uniform: every thread holds the same bracket)
@@ -330,6 +358,7 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
     const double pivmin = fmax(tnorm * 2.3e-16, 1e-290);
     const int invit_iters = g_invit_iters;
     for (int iter = 0; iter < invit_iters; iter++) {
+        double sc = 1.0;
         if (warp < 8 && lane == 0) {
             const int w = warp;
             const double l = lam[w];
@@ -374,8 +403,12 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
                 z2 = z1; z1 = t;
                 zmax = fmax(zmax, fabs(t));
             }
-            double sc = zmax > 0 ? 1.0 / zmax : 1.0;                  // avoid overflow in the dot products
-            for (int i = 0; i < n; i++) z[i] *= sc;
+            sc = zmax > 0 ? 1.0 / zmax : 1.0;                         // avoid overflow in the dot products
+        }
+        if (warp < 8) {                                               // the whole warp applies lane 0's scale
+            sc = __shfl_sync(0xffffffffu, sc, 0);
+            double* z = zs + warp * n;
+            for (int i = lane; i < n; i += 32) z[i] *= sc;
         }
         __syncthreads();
         // Gram-Schmidt in ascending order + normalisation: warp p < w forms <z_p, z_w>, then one fused update
@@ -427,6 +460,8 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
         for (int i = tid; i < n; i += EIG_THREADS) z[i] = __ldcg(gvec + (int64_t)w * n + i);
         const double lamw = __ldcg(lam_g + w);
         int pp = 0;
+        const bool act = warp * 32 < n;                         // this warp owns at least one row
+        if (!act && lane < 6) part[lane & 1][lane >> 1][warp] = 0.0;      // its partial sums stay zero
         for (int khi = n - 3; khi >= 0; khi -= srows) {
             const int klo = khi - (srows - 1) > 0 ? khi - (srows - 1) : 0;
             __syncthreads();                                    // the previous block of reflectors is no longer read
@@ -442,35 +477,51 @@ k_eig_top8(const float* __restrict__ M, int n, double* __restrict__ A, double* _
             for (; k - 1 >= klo; k -= 2) {
                 // reflectors k (applied first) and k-1 in ONE barrier round: with p = v_k.z, q = v_{k-1}.z, r = v_{k-1}.v_k
                 //   a_k = beta_k p,   a_{k-1} = beta_{k-1} (q - a_k r),   z -= a_k v_k + a_{k-1} v_{k-1}
-                const double bk = sbeta[k - klo], bm = sbeta[k - 1 - klo];
+                // (the fp64 pipe is what this loop waits for: the reductions are arranged for few fp64 instructions, and
+                //  warps that own no row only keep the barriers)
                 const double* vk = stage + (k - klo) * n - (k + 1);         // vk[j]: component of row j (rows j > k)
                 const double* vm = stage + (k - 1 - klo) * n - k;           // vm[j]: rows j > k-1
-                double pa = 0.0, qa = 0.0, ra = 0.0;
-                for (int j = tid; j < n; j += EIG_THREADS) {
-                    if (j > k) { const double a = vk[j], b = vm[j], zz = z[j]; pa += a * zz; qa += b * zz; ra += a * b; }
-                    else if (j == k) qa += vm[j] * z[j];
+                if (act) {
+                    double pa = 0.0, qa = 0.0, ra = 0.0;
+                    for (int j = tid; j < n; j += EIG_THREADS) {
+                        if (j > k) { const double a = vk[j], b = vm[j], zz = z[j]; pa += a * zz; qa += b * zz; ra += a * b; }
+                        else if (j == k) qa += vm[j] * z[j];
+                    }
+                    const double pq = warp_sum_pair(pa, qa, lane);          // lanes < 16: sum of pa, lanes >= 16: sum of qa
+                    ra = warp_sum(ra);
+                    if ((lane & 15) == 0) part[pp][lane >> 4][warp] = pq;
+                    if (lane == 0) part[pp][2][warp] = ra;
                 }
-                pa = warp_sum(pa); qa = warp_sum(qa); ra = warp_sum(ra);
-                if (lane == 0) { part[pp][0][warp] = pa; part[pp][1][warp] = qa; part[pp][2][warp] = ra; }
                 __syncthreads();
-                const double ak = bk * tree16(part[pp][0]);
-                const double am = bm * (tree16(part[pp][1]) - ak * tree16(part[pp][2]));
-                for (int j = tid; j < n; j += EIG_THREADS) {
-                    if (j > k) z[j] -= ak * vk[j] + am * vm[j];
-                    else if (j == k) z[j] -= am * vm[j];
+                if (act) {
+                    double pq = part[pp][lane >> 4][lane & 15], rr = part[pp][2][lane & 15];
+#pragma unroll
+                    for (int o = 8; o; o >>= 1) { pq += __shfl_xor_sync(0xffffffffu, pq, o); rr += __shfl_xor_sync(0xffffffffu, rr, o); }
+                    const double ak = sbeta[k - klo] * __shfl_sync(0xffffffffu, pq, 0);
+                    const double am = sbeta[k - 1 - klo] * (__shfl_sync(0xffffffffu, pq, 16) - ak * rr);
+                    for (int j = tid; j < n; j += EIG_THREADS) {
+                        if (j > k) z[j] -= ak * vk[j] + am * vm[j];
+                        else if (j == k) z[j] -= am * vm[j];
+                    }
                 }
                 pp ^= 1;
             }
             if (k >= klo) {                                     // odd one left in this block
-                const double bt = sbeta[k - klo];
                 const double* v = stage + (k - klo) * n - (k + 1);
-                double a = 0.0;
-                for (int j = tid; j < n; j += EIG_THREADS) if (j > k) a += v[j] * z[j];
-                a = warp_sum(a);
-                if (lane == 0) part[pp][0][warp] = a;
+                if (act) {
+                    double a = 0.0;
+                    for (int j = tid; j < n; j += EIG_THREADS) if (j > k) a += v[j] * z[j];
+                    a = warp_sum(a);
+                    if (lane == 0) part[pp][0][warp] = a;
+                }
                 __syncthreads();
-                const double t = bt * tree16(part[pp][0]);
-                for (int j = tid; j < n; j += EIG_THREADS) if (j > k) z[j] -= t * v[j];
+                if (act) {
+                    double t = part[pp][0][lane & 15];
+#pragma unroll
+                    for (int o = 8; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+                    t *= sbeta[k - klo];
+                    for (int j = tid; j < n; j += EIG_THREADS) if (j > k) z[j] -= t * v[j];
+                }
                 pp ^= 1;
             }
         }
