@@ -704,6 +704,23 @@ int dmp2_resblock(dmp2_engine* e, int block, const float* x_nhwc_dev, int L, flo
     return 0;
 }
 
+int dmp2_stem(dmp2_engine* e, const float* mat1d_t_dev, const float* feat_dev, const float* dmap_dev, int L, float* out_nhwc_dev,
+              void* stream) {
+    STAGE_PROLOGUE(L, 1);
+    if (!mat1d_t_dev || !feat_dev || !dmap_dev || !out_nhwc_dev) return e->fail(DMP2_ERR_BAD_ARG, "stem: null pointer");
+    TRY(run_feat_import(e, feat_dev, L, e->ws.feat, st));
+    TRY(run_stem_base(e, mat1d_t_dev, e->ws.feat, L, st));
+    TRY(run_stem_update(e, dmap_dev, L, st));
+    CUDA_TRY(e, cudaMemcpyAsync(out_nhwc_dev, e->ws.x, (size_t)L * L * 128 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+int dmp2_head(dmp2_engine* e, const float* x_nhwc_dev, int L, float* head_out_dev, void* stream) {
+    STAGE_PROLOGUE(L, 1);
+    if (!x_nhwc_dev || !head_out_dev) return e->fail(DMP2_ERR_BAD_ARG, "head: null pointer");
+    return run_head(e, x_nhwc_dev, L, head_out_dev, st);
+}
+
 int dmp2_resnet_pass(dmp2_engine* e, const float* mat1d_t_dev, const float* feat_dev, const float* dmap_dev, int L,
                      float* head_out_dev, void* stream) {
     STAGE_PROLOGUE(L, 1);

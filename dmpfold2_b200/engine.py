@@ -48,6 +48,8 @@ _SIGS = {
     'dmp2_hgru': (_i, [_vp, _vp, _i, _vp, _vp]),
     'dmp2_conv5_maxout': (_i, [_vp, _i, _vp, _i, _vp, _vp]),
     'dmp2_resblock': (_i, [_vp, _i, _vp, _i, _vp, _vp]),
+    'dmp2_stem': (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    'dmp2_head': (_i, [_vp, _vp, _i, _vp, _vp]),
     'dmp2_resnet_pass': (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp]),
     'dmp2_head_mds': (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
     'dmp2_eig_top8': (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
@@ -312,6 +314,24 @@ class Engine:
         l = x.shape[0]
         out = self._empty(l, l, 128)
         self._check(self.lib.dmp2_resblock(self.h, block, _ptr(x), l, _ptr(out), self._stream()), 'dmp2_resblock')
+        return out
+
+    def stem(self, mat1d_t, feat, dmap) -> torch.Tensor:
+        """network.py:194 on the never-materialised 955-channel input of network.py:227-229 -> (L, L, 128) NHWC."""
+        m = self._dev(mat1d_t, torch.float32)
+        f = self._dev(feat, torch.float32)
+        d = self._dev(dmap, torch.float32)
+        l = m.shape[0]
+        out = self._empty(l, l, 128)
+        self._check(self.lib.dmp2_stem(self.h, _ptr(m), _ptr(f), _ptr(d), l, _ptr(out), self._stream()), 'dmp2_stem')
+        return out
+
+    def head(self, x_nhwc) -> torch.Tensor:
+        """network.py:207 (resnet.17): (L, L, 128) NHWC -> (2, L, L)."""
+        x = self._dev(x_nhwc, torch.float32)
+        l = x.shape[0]
+        out = self._empty(2, l, l)
+        self._check(self.lib.dmp2_head(self.h, _ptr(x), l, _ptr(out), self._stream()), 'dmp2_head')
         return out
 
     def resnet_pass(self, mat1d_t, feat, dmap) -> torch.Tensor:

@@ -143,6 +143,13 @@ int dmp2_hgru(dmp2_engine* e, const float* in_dev, int L, float* out_dev, void* 
 int dmp2_conv5_maxout(dmp2_engine* e, int block, const float* x_nhwc_dev, int L, float* out_nhwc_dev, void* stream);
 /* network.py:94-103  one full ResNet_Block: x (L*L,128) NHWC -> (L*L,128) NHWC */
 int dmp2_resblock(dmp2_engine* e, int block, const float* x_nhwc_dev, int L, float* out_nhwc_dev, void* stream);
+/* network.py:194 (resnet.0 = Maxout2d(955 -> 128, pool 3, k=1), network.py:25-34) on the concatenated input of
+ * network.py:227-229, which is never materialised: mat1d_t (L,512) time-major hgru output, feat (L,L,442), dmap (L,L)
+ * -> the stem output (L*L, 128) NHWC fp32 = the input of ResNet block 1. */
+int dmp2_stem(dmp2_engine* e, const float* mat1d_t_dev, const float* feat_dev, const float* dmap_dev, int L,
+              float* out_nhwc_dev, void* stream);
+/* network.py:207 (resnet.17, the final 1x1 conv 128 -> 2): x (L*L, 128) NHWC fp32 -> head (2, L, L) */
+int dmp2_head(dmp2_engine* e, const float* x_nhwc_dev, int L, float* head_out_dev, void* stream);
 /* network.py:229-235  one ResNet pass from its inputs: mat1d_t (L,512) time-major hgru output, feat (L,L,442),
  * dmap (L,L) -> head (2, L, L) like resnet.17's output. */
 int dmp2_resnet_pass(dmp2_engine* e, const float* mat1d_t_dev, const float* feat_dev, const float* dmap_dev, int L,

@@ -163,6 +163,37 @@ def test_resnet_pass_teacher_forced(eng, oracle, pf10963, mode, tol):
 
 
 @needs_weights
+@pytest.mark.parametrize('gemm', ['tc', 'ffma'])
+def test_stem_and_head_teacher_forced(state_dict, oracle, pf10963, gemm, monkeypatch):
+    # SURVEY 8(b) stage list: dmp2_stem (network.py:194 on the 955-channel input of :227-229) and dmp2_head (network.py:207)
+    from dmpfold2_b200.engine import Engine
+    monkeypatch.setenv('DMP2_GEMM', gemm)
+    taps = {}
+    oracle.fold(pf10963, iterations=0, minsteps=0, taps=taps)
+    x2 = taps['x2'][0]
+    feat = x2[:442].permute(1, 2, 0).contiguous()
+    e = Engine(state_dict, 0)
+    try:
+        got = e.stem(taps['mat1d'].t().contiguous(), feat, x2[442]).cpu()
+        ref = _nhwc(taps['stem'])
+        assert _rel(got, ref) < 1e-4, _rel(got, ref)
+        head = e.head(_nhwc(taps['block16'])).cpu()
+        assert _rel(head, taps['head'][0]) < 1e-5, _rel(head, taps['head'][0])
+        # the recycling input (network.py:264-270): channel 954 becomes the distance map of the previous coordinates
+        ca = taps['ca0']
+        dmap = torch.clamp((ca.unsqueeze(0) - ca.unsqueeze(1)).pow(2).sum(dim=2), min=1e-8).sqrt()
+        m1 = taps['mat1d']
+        resinp = torch.cat(((m1.unsqueeze(1) * m1.unsqueeze(2)).unsqueeze(0), x2[None, :442], dmap[None, None]), dim=1)
+        sd = oracle.sd
+        ref2 = O.maxout_norm(resinp, sd['resnet.0.lin.weight'], sd['resnet.0.lin.bias'], sd['resnet.0.norm.weight'],
+                             sd['resnet.0.norm.bias'], 3, 0)
+        got2 = e.stem(m1.t().contiguous(), feat, dmap).cpu()
+        assert _rel(got2, _nhwc(ref2)) < 1e-4, _rel(got2, _nhwc(ref2))
+    finally:
+        e.close()
+
+
+@needs_weights
 def test_head_mds_on_golden_head(eng):
     g = np.load(os.path.join(GOLDEN, 'pf10963_n0_m0.npz'))
     head = torch.from_numpy(g['head'])
