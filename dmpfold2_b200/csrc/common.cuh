@@ -236,6 +236,27 @@ struct dmp2_engine {
     bool profile = false;            // record a CUDA-event pair around every conv launch (bench.py roofline)
     std::vector<cudaEvent_t> prof_ev;
     size_t prof_used = 0;
+    // CUDA-graph replay of the recycling iterations (network.py:264-306; dmp2_set_graph / DMP2_GRAPH=1): iteration = distance
+    // map -> ResNet pass -> head -> eigen step -> coordinate GRU -> best-of-n select is the same ~60 launches on the same
+    // buffers every time, so it is captured once per (L, workspace, kernel configuration) and replayed `iterations` times.
+    bool graph_on = false;
+    bool capturing = false;          // true while the iteration is being captured (conv launcher: self-resetting unit counter)
+    cudaStream_t cap_stream = nullptr;
+    cudaGraphExec_t pass_exec = nullptr;
+    int64_t pass_nodes = 0;          // kernel launches one replay stands for (gpu_launches bookkeeping)
+    uint64_t ws_gen = 0;             // bumped whenever the workspace is (re)allocated: every captured pointer is stale then
+    struct PassKey {
+        int L = 0, conv_mode = -1, conv_cluster = -1, conv_chunk_taps = -1, conv_sms = -1;
+        bool conv_dynamic = false, gemm_tc = false, fuse_stats = false, eig_no_cl16 = false, profile = false;
+        uint64_t ws_gen = 0;
+        bool operator==(const PassKey& o) const {
+            return L == o.L && conv_mode == o.conv_mode && conv_cluster == o.conv_cluster && conv_chunk_taps == o.conv_chunk_taps &&
+                   conv_sms == o.conv_sms && conv_dynamic == o.conv_dynamic && gemm_tc == o.gemm_tc && fuse_stats == o.fuse_stats &&
+                   eig_no_cl16 == o.eig_no_cl16 && profile == o.profile && ws_gen == o.ws_gen;
+        }
+    } pass_key;
+    std::vector<cudaEvent_t> gprof_ev;   // event pairs recorded by the graph's conv nodes when profiling (2 per block)
+    bool gprof_valid = false;            // the graph has been replayed since dmp2_conv_profile last looked
 
     int fail(int code, const std::string& msg) {
         status = code;

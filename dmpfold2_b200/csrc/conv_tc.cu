@@ -107,6 +107,10 @@ struct TcParams {
     // [sched_base, sched_base + units + clusters) (every cluster makes exactly one failing claim).
     unsigned long long* sched;
     unsigned long long sched_base;
+    // launches captured into a CUDA graph are replayed with frozen arguments: they use a second counter that the launch
+    // itself puts back to sched_base (the cluster that draws the last of the units + clusters values knows every other
+    // claim has been made)
+    int sched_reset;
 };
 constexpr int STAT_GROUP = 16;   // CTAs per first-level fold
 constexpr int UQ = 4;            // depth of the claimed-unit queue (the roles of a cluster are never 4 units apart, see unit_at)
@@ -256,6 +260,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv5_tc(const __grid_consta
     auto post_unit = [&](int i, unsigned long long raw) {                                // one lane of rank 0's producer warp
         const unsigned long long rel = raw - p.sched_base;
         const int v = rel < (unsigned long long)p.units ? (int)rel : p.units;
+        if (p.sched_reset && rel == (unsigned long long)(p.units + num_clusters - 1)) atomicExch(p.sched, p.sched_base);
 #pragma unroll
         for (int rk = 0; rk < CL; rk++) {
             const uint32_t rb = CL > 1 ? mapa_u32(uq_full(i & (UQ - 1)), rk) : uq_full(i & (UQ - 1));
@@ -655,7 +660,12 @@ int launch_mode(dmp2_engine* e, int mode, int form, const ConvMaps& maps, TcPara
     int sms = e->conv_sms > 0 ? std::min(e->conv_sms, e->num_sms) : e->num_sms;
     int grid = std::min(sms / cl, p.units) * cl;
     if (grid < cl) grid = cl;
-    if (p.sched) {                                   // this launch owns the next units + clusters counter values
+    p.sched_reset = 0;
+    if (p.sched && e->capturing) {                   // graph node: frozen arguments, so a counter the launch itself rewinds
+        p.sched = e->ws.sched + 1;
+        p.sched_base = 0;
+        p.sched_reset = 1;
+    } else if (p.sched) {                            // this launch owns the next units + clusters counter values
         p.sched_base = e->conv_sched_base;
         e->conv_sched_base += (unsigned long long)p.units + (unsigned long long)(grid / cl);
     }

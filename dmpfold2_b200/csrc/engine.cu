@@ -231,9 +231,18 @@ static int load_weights(dmp2_engine* e, HostSD& sd) {
 // ---------------------------------------------------------------------------------------------------
 // workspace
 // ---------------------------------------------------------------------------------------------------
+static void drop_pass_graph(dmp2_engine* e) {
+    if (e->pass_exec) cudaGraphExecDestroy(e->pass_exec);
+    e->pass_exec = nullptr;
+    e->pass_nodes = 0;
+    e->gprof_valid = false;
+}
+
 static void free_workspace(dmp2_engine* e) {
     conv_tc_invalidate(e);               // cached tensor maps point into the buffers released here
     vgru_tc_invalidate(e);
+    drop_pass_graph(e);                  // ... and so does every node of the captured recycling iteration
+    e->ws_gen++;
     for (void* p : e->ws.allocs) cudaFree(p);
     e->ws = Workspace();
 }
@@ -355,6 +364,77 @@ static int one_pass(dmp2_engine* e, int L, cudaStream_t st) {
     return 0;
 }
 
+// one recycling iteration (network.py:265-306): distance map of the current coordinates -> pass -> keep the best
+static int recycle_once(dmp2_engine* e, int L, cudaStream_t st) {
+    Workspace& ws = e->ws;
+    TRY(run_dmap(e, ws.ca, L, ws.dmap, true, st));
+    TRY(one_pass(e, L, st));
+    return run_select(e, ws.ca, ws.conf, L, 0, st);
+}
+
+// Largest L whose eigen step is a plain cluster launch; beyond it run_eig_top8 uses a cooperative whole-GPU launch,
+// which is left out of graphs.
+#define DMP2_GRAPH_MAX_L 600
+
+// Capture one recycling iteration on the engine's capture stream and instantiate it.  Every launch of the iteration
+// reads and writes workspace buffers only, and no host-side value changes between iterations, so the captured nodes
+// are valid until the workspace or the kernel configuration changes (PassKey).  Returns 0 with e->pass_exec == nullptr
+// when capture is not possible here (the caller then runs the iterations eagerly).
+static int capture_pass(dmp2_engine* e, int L) {
+    drop_pass_graph(e);
+    if (!e->cap_stream) CUDA_TRY(e, cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
+    if (e->profile && e->gprof_ev.empty()) {
+        e->gprof_ev.resize(2 * DMP2_NBLOCKS);
+        for (auto& ev : e->gprof_ev) CUDA_TRY(e, cudaEventCreate(&ev));
+    }
+    const int64_t l0 = e->launches;
+    if (cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        e->graph_on = false;
+        return 0;
+    }
+    e->capturing = true;
+    const int rc = recycle_once(e, L, e->cap_stream);
+    e->capturing = false;
+    cudaGraph_t g = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(e->cap_stream, &g);
+    const int64_t nodes = e->launches - l0;
+    e->launches = l0;                                   // nothing has run yet
+    cudaGraphExec_t exec = nullptr;
+    if (rc == 0 && ce == cudaSuccess && g && cudaGraphInstantiate(&exec, g, 0) == cudaSuccess) {
+        e->pass_exec = exec;
+        e->pass_nodes = nodes;
+    } else {                                            // not capturable on this driver / configuration: stay eager from now on
+        cudaGetLastError();
+        e->status = 0;
+        e->err.clear();
+        e->graph_on = false;
+    }
+    if (g) cudaGraphDestroy(g);
+    return 0;
+}
+
+static int recycle(dmp2_engine* e, int L, int iterations, cudaStream_t st) {
+    if (e->graph_on && iterations >= 2 && !e->strip_on && L <= DMP2_GRAPH_MAX_L) {
+        dmp2_engine::PassKey k;
+        k.L = L; k.conv_mode = e->conv_mode; k.conv_cluster = e->conv_cluster; k.conv_chunk_taps = e->conv_chunk_taps;
+        k.conv_sms = e->conv_sms; k.conv_dynamic = e->conv_dynamic; k.gemm_tc = e->gemm_tc; k.fuse_stats = e->fuse_stats;
+        k.eig_no_cl16 = e->eig_no_cl16; k.profile = e->profile; k.ws_gen = e->ws_gen;
+        if (!e->pass_exec || !(e->pass_key == k)) {
+            TRY(capture_pass(e, L));
+            e->pass_key = k;
+        }
+        if (e->pass_exec) {
+            for (int it = 0; it < iterations; it++) CUDA_TRY(e, cudaGraphLaunch(e->pass_exec, st));
+            e->launches += e->pass_nodes * iterations;
+            if (e->profile) e->gprof_valid = true;
+            return 0;
+        }
+    }
+    for (int it = 0; it < iterations; it++) TRY(recycle_once(e, L, st));
+    return 0;
+}
+
 static int fold_impl(dmp2_engine* e, const uint8_t* msa, int N, int L, const float* tmpl, int iterations, int minsteps,
                      float* coords_out, float* conf_out, cudaStream_t st, bool timed) {
     if (!msa || !coords_out || !conf_out) return e->fail(DMP2_ERR_BAD_ARG, "fold: null pointer");
@@ -400,11 +480,7 @@ static int fold_impl(dmp2_engine* e, const uint8_t* msa, int N, int L, const flo
     TRY(one_pass(e, L, st));                                          // network.py:235-255
     if (minsteps > 0) TRY(run_refine(e, ws.ca, L, minsteps, st));     // network.py:257-258
     TRY(run_select(e, ws.ca, ws.conf, L, 1, st));
-    for (int it = 0; it < iterations; it++) {                         // network.py:264-306
-        TRY(run_dmap(e, ws.ca, L, ws.dmap, true, st));
-        TRY(one_pass(e, L, st));
-        TRY(run_select(e, ws.ca, ws.conf, L, 0, st));
-    }
+    TRY(recycle(e, L, iterations, st));                               // network.py:264-306
     mark();
     if (minsteps > 0) TRY(run_refine(e, ws.best_ca, L, minsteps, st)); // network.py:308-309
     TRY(run_backbone(e, ws.best_ca, ws.best_conf, L, coords_out, conf_out, st));
@@ -454,6 +530,7 @@ int dmp2_create(dmp2_engine** out, int device, int n_tensors, const char* const*
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
         const char* sp = getenv("DMP2_SIDE_PRIORITY");
         if (sp && !strcmp(sp, "default")) cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking);
+        else if (sp && !strcmp(sp, "high")) cudaStreamCreateWithPriority(&e->side, cudaStreamNonBlocking, hi);   // tuning knob: features first
         else cudaStreamCreateWithPriority(&e->side, cudaStreamNonBlocking, lo);
     }
     cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming);
@@ -478,6 +555,8 @@ int dmp2_create(dmp2_engine** out, int device, int n_tensors, const char* const*
     const char* vm = getenv("DMP2_VGRU");
     const char* gm = getenv("DMP2_GEMM");
     if (gm && !strcmp(gm, "ffma")) e->gemm_tc = false;
+    const char* gr = getenv("DMP2_GRAPH");
+    if (gr) e->graph_on = strcmp(gr, "0") != 0;
     const char* fs = getenv("DMP2_FUSE_STATS");
     if (fs) e->fuse_stats = strcmp(fs, "0") != 0;
     if (vm && !strcmp(vm, "ffma")) e->vgru_mode = 1;
@@ -500,6 +579,8 @@ void dmp2_destroy(dmp2_engine* e) {
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->ev_join) cudaEventDestroy(e->ev_join);
     for (auto& ev : e->prof_ev) cudaEventDestroy(ev);
+    for (auto& ev : e->gprof_ev) cudaEventDestroy(ev);
+    if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
     delete e;
 }
 
@@ -551,7 +632,16 @@ int dmp2_conv_profile(dmp2_engine* e, int* n_launches, float* total_ms) {
         CUDA_TRY(e, cudaEventElapsedTime(&ms, e->prof_ev[i], e->prof_ev[i + 1]));
         tot += ms;
     }
-    *n_launches = (int)(e->prof_used / 2);
+    int n = (int)(e->prof_used / 2);
+    if (e->gprof_valid) {                              // the conv nodes of the last graph replay (a sample: replays overwrite them)
+        for (size_t i = 0; i + 1 < e->gprof_ev.size(); i += 2) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, e->gprof_ev[i], e->gprof_ev[i + 1]) == cudaSuccess) { tot += ms; n++; }
+            else cudaGetLastError();
+        }
+        e->gprof_valid = false;
+    }
+    *n_launches = n;
     *total_ms = tot;
     e->prof_used = 0;
     return 0;
@@ -776,6 +866,12 @@ int dmp2_set_vgru_input(dmp2_engine* e, const float* vgru_dev) {
 int dmp2_set_conv_dynamic(dmp2_engine* e, int on) {
     if (!e) return DMP2_ERR_BAD_ARG;
     e->conv_dynamic = on != 0;
+    return 0;
+}
+
+int dmp2_set_graph(dmp2_engine* e, int on) {
+    if (!e) return DMP2_ERR_BAD_ARG;
+    e->graph_on = on != 0;
     return 0;
 }
 

@@ -333,9 +333,12 @@ int run_conv_ffma(dmp2_engine* e, int blk, const float* x, int L, float* raw, cu
 // One ResNet block in place on ws.x (and its fp16 split ws.xh/xl).
 int run_resblock(dmp2_engine* e, int blk, int L, cudaStream_t st) {
     Workspace& ws = e->ws;
-    const bool prof = e->profile && e->prof_used + 2 <= e->prof_ev.size();
+    // captured into the recycling graph: the graph owns one event pair per block (re-recorded by every replay)
+    const bool gprof = e->capturing && e->profile && e->gprof_ev.size() >= (size_t)2 * DMP2_NBLOCKS;
+    const bool prof = !e->capturing && e->profile && e->prof_used + 2 <= e->prof_ev.size();
     const bool fused = conv_tc_fuses_stats(e);
     if (prof) cudaEventRecord(e->prof_ev[e->prof_used], st);
+    if (gprof) cudaEventRecord(e->gprof_ev[2 * blk], st);
     if (e->strip_on) {
         // strip of R rows; the activation copies carry 2 halo rows on each side, filled by the neighbours
         const Rows rw = rows_of(e, L);
@@ -346,6 +349,7 @@ int run_resblock(dmp2_engine* e, int blk, int L, cudaStream_t st) {
     } else if (e->conv_mode == DMP2_CONV_FFMA) TRY(run_conv_ffma(e, blk, ws.x, L, ws.raw, st));
     else TRY(run_conv_tc(e, blk, ws.xh, ws.xl, ws.x8lo, ws.x8hi, L, L, 0, L, ws.raw, e->conv_mode, st, fused));
     if (prof) { cudaEventRecord(e->prof_ev[e->prof_used + 1], st); e->prof_used += 2; }
+    if (gprof) cudaEventRecord(e->gprof_ev[2 * blk + 1], st);
     return run_norm_gate(e, blk, ws.raw, ws.x, L, false, st, fused && e->conv_mode != DMP2_CONV_FFMA);
 }
 

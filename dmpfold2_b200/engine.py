@@ -58,6 +58,7 @@ _SIGS = {
     'dmp2_backbone': (_i, [_vp, _vp, _i, _vp, _vp]),
     'dmp2_gemm_tn_test': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     'dmp2_set_conv_sms': (_i, [_vp, _i]),
+    'dmp2_set_graph': (_i, [_vp, _i]),
     'dmp2_set_conv_dynamic': (_i, [_vp, _i]),
     'dmp2_set_vgru_input': (_i, [_vp, _vp]),
 }
@@ -390,6 +391,11 @@ class Engine:
 
     def set_conv_sms(self, sms: int):
         self._check(self.lib.dmp2_set_conv_sms(self.h, int(sms)), 'dmp2_set_conv_sms')
+
+    def set_graph(self, on: bool = True):
+        """Replay the recycling iterations (network.py:264-306) from a CUDA graph captured once per (L, workspace,
+        kernel configuration) instead of re-enqueueing their ~60 launches each time; bit-identical results."""
+        self._check(self.lib.dmp2_set_graph(self.h, 1 if on else 0), 'dmp2_set_graph')
 
     def set_conv_dynamic(self, on: bool = True):
         """Dynamic unit schedule of the persistent conv kernel (several folds in flight on one GPU, see dmp2.h)."""

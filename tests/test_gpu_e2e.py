@@ -242,3 +242,53 @@ def test_fused_stats_variant(state_dict, pf10963, monkeypatch):
     e1.close()
     assert O.kabsch_rmsd(c1[:, 1], c0[:, 1]) < 1e-5 and np.abs(f1 - f0).max() < 1e-5
     assert np.isfinite(c1).all() and n_fused > 0
+
+
+@needs_weights
+@pytest.mark.parametrize('dynamic', [False, True])
+def test_graph_replay_of_the_recycling_iterations(state_dict, pf10963, dynamic):
+    """dmp2_set_graph: the recycling iterations (network.py:264-306) replayed from a CUDA graph captured once per
+    (L, workspace, configuration) give the eager loop's result -- bit for bit with the static conv schedule -- and the
+    launch bookkeeping, a change of L, a change of conv mode and the conv profiler keep working."""
+    from dmpfold2_b200.engine import Engine
+    e = Engine(state_dict, 0)
+    try:
+        e.set_conv_dynamic(dynamic)
+        n0 = e.launch_count
+        a = e.fold_host(pf10963, None, 4, 10)
+        per_fold = e.launch_count - n0
+        e.set_graph(True)
+        b = e.fold_host(pf10963, None, 4, 10)              # captures the iteration, replays it 4 times
+        c = e.fold_host(pf10963, None, 4, 10)              # replays the cached graph
+        assert e.launch_count - n0 == 3 * per_fold         # a replay counts the launches it stands for
+        if dynamic:                                        # which CTA sums which unit varies: fp64 statistics to rounding
+            assert O.kabsch_rmsd(a[0][:, 1], b[0][:, 1]) < 1e-4 and O.kabsch_rmsd(a[0][:, 1], c[0][:, 1]) < 1e-4
+        else:
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+            assert np.array_equal(a[0], c[0]) and np.array_equal(a[1], c[1])
+        g = np.load(os.path.join(GOLDEN, 'pf10963_n10_m100.npz'))
+        coords, conf = e.fold_host(pf10963, None, 10, 100)
+        _check(coords, conf, g)
+        # another alignment length and another conv mode re-capture
+        msa2 = np.ascontiguousarray(pf10963[:90, :57])
+        d1 = e.fold_host(msa2, None, 3, 5)
+        e.set_conv_mode('f16x3')
+        f1 = e.fold_host(msa2, None, 3, 5)
+        e.set_graph(False)
+        f0 = e.fold_host(msa2, None, 3, 5)
+        e.set_conv_mode('f16f8')
+        d0 = e.fold_host(msa2, None, 3, 5)
+        if not dynamic:
+            assert np.array_equal(d0[0], d1[0]) and np.array_equal(f0[0], f1[0])
+        else:
+            assert O.kabsch_rmsd(d0[0][:, 1], d1[0][:, 1]) < 1e-4 and O.kabsch_rmsd(f0[0][:, 1], f1[0][:, 1]) < 1e-4
+        # conv profiler with the graph on: eager first pass (16 launches) + the graph's last replay (16 launches)
+        e.set_graph(True)
+        e.set_profile(True)
+        e.fold_host(pf10963, None, 4, 10)
+        n, ms = e.conv_profile()
+        e.set_profile(False)
+        print(f'conv launches timed with the graph on: {n}, mean {ms / max(n, 1) * 1e3:.1f} us')
+        assert n in (16, 32) and 0.0 < ms / n < 5.0, (n, ms)   # 16: this driver does not time event-record nodes
+    finally:
+        e.close()
