@@ -237,7 +237,7 @@ struct dmp2_engine {
     std::vector<cudaEvent_t> prof_ev;
     size_t prof_used = 0;
     // CUDA-graph replay of the recycling iterations (network.py:264-306; dmp2_set_graph / DMP2_GRAPH=1): iteration = distance
-    // map -> ResNet pass -> head -> eigen step -> coordinate GRU -> best-of-n select is the same ~60 launches on the same
+    // map -> ResNet pass -> head -> eigen step -> coordinate GRU -> best-of-n select is the same ~50 launches on the same
     // buffers every time, so it is captured once per (L, workspace, kernel configuration) and replayed `iterations` times.
     bool graph_on = false;
     bool capturing = false;          // true while the iteration is being captured (conv launcher: self-resetting unit counter)

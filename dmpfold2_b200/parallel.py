@@ -113,12 +113,14 @@ class StreamPool:
     * conv_dynamic (default: on when streams > 1): the conv kernel claims its work units from a device counter, so a
       launch that finds SMs occupied by another target's kernels is finished by the CTAs that did start
       (dmp2_set_conv_dynamic).
-    * scan_rows (default 384 = one wave of the vgru kernel; 0 = off): the vgru scan (network.py:223-224) is N dependent
+    * scan_rows (default 384 = one wave of the vgru kernel when streams > 1; 0 = off, the default for one stream): the vgru scan (network.py:223-224) is N dependent
       steps that each occupy ~all SMs for ~14 us, mostly waiting, whatever the alignment length up to 384 columns.  It is
       independent per alignment column, so the pool scans the columns of consecutive targets with the same N in ONE call
       on a separate engine and hands every fold its slice (dmp2_set_vgru_input): bit-identical, and the scan costs the
       batch what it used to cost one target.
     * conv_sms < #SMs keeps a few SMs free of the persistent conv kernel.
+    * graph=True replays every engine's recycling iterations from a CUDA graph (dmp2_set_graph): a third less host time per
+      fold for the enqueueing threads, same device time (None = the engines' default, DMP2_GRAPH).
 
     engine_factory(i) -> engine lets the CPU tests (and other back ends) substitute the engine; an engine needs
     fold(msa, template, iterations, minsteps) -> (coords, confs), set_conv_sms(n) and close().
@@ -126,7 +128,7 @@ class StreamPool:
 
     def __init__(self, state_dict=None, device_index: int = 0, streams: int = 2, conv_mode: Optional[str] = None,
                  conv_sms: int = 0, engine_factory: Optional[Callable[[int], object]] = None,
-                 conv_dynamic: Optional[bool] = None, scan_rows: int = 384):
+                 conv_dynamic: Optional[bool] = None, scan_rows: Optional[int] = None, graph: Optional[bool] = None):
         if streams < 1:
             raise ValueError('streams must be >= 1')
         if engine_factory is None:
@@ -145,7 +147,13 @@ class StreamPool:
             for e in self.engines:
                 if hasattr(e, 'set_conv_dynamic'):
                     e.set_conv_dynamic(True)
-        self.scan_rows = int(scan_rows)
+        # shared scans pay when other streams' folds fill the GPU meanwhile; with ONE stream the scan stream only competes with
+        # the fold it feeds (measured at the cfg3 shape: 53.5 ms/target with, 39.5 without -- profiles/round2_graph_replay.txt)
+        self.scan_rows = (384 if streams > 1 else 0) if scan_rows is None else int(scan_rows)
+        if graph is not None:
+            for e in self.engines:
+                if hasattr(e, 'set_graph'):
+                    e.set_graph(bool(graph))
         self._scan_engine = None
         self._scan_stream = None
         self._streams = None

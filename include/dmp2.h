@@ -76,7 +76,7 @@ int dmp2_stage_times(const dmp2_engine* e, float* out_ms, int cap);
 int dmp2_debug_eig_phases(dmp2_engine* e, int L, double* out_us, int cap);
 
 /* CUDA-graph replay of the recycling iterations (network.py:264-306): when on, one iteration (distance map -> ResNet
- * pass -> head -> eigen step -> coordinate GRU -> best-of-n select, ~60 launches on fixed workspace buffers) is captured
+ * pass -> head -> eigen step -> coordinate GRU -> best-of-n select, ~50 launches on fixed workspace buffers) is captured
  * once per (L, workspace, kernel configuration) and replayed `iterations` times; results are bit-identical to the eager
  * loop.  Used for L <= 600 and iterations >= 2; falls back to eager launches where capture is refused.
  * Off by default (environment: DMP2_GRAPH=1). */

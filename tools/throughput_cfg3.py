@@ -31,7 +31,7 @@ ap.add_argument('--N', type=int, default=512)
 ap.add_argument('--streams', type=str, default='1,2,3,4')
 ap.add_argument('--conv-sms', type=int, default=0)
 ap.add_argument('--conv-mode', type=str, default='f16f8')
-ap.add_argument('--scan-rows', type=int, default=384, help='alignment columns per shared vgru scan (0 = every fold scans its own)')
+ap.add_argument('--scan-rows', type=int, default=-1, help='alignment columns per shared vgru scan (0 = every fold scans its own; -1 = StreamPool default: 384 when streams > 1)')
 ap.add_argument('--host-threads', type=int, default=1, help='1: one enqueueing host thread per stream; 0: a single thread')
 ap.add_argument('--dynamic', type=int, default=-1, help='conv unit schedule: 1 dynamic, 0 static, -1 StreamPool default (dynamic when streams > 1)')
 args = ap.parse_args()
@@ -57,7 +57,7 @@ def barrier():
 
 for k in [int(x) for x in args.streams.split(',')]:
     pool = P.StreamPool(sd, local_rank, streams=k, conv_mode=args.conv_mode, conv_sms=args.conv_sms,
-                        conv_dynamic=None if args.dynamic < 0 else bool(args.dynamic), scan_rows=args.scan_rows)
+                        conv_dynamic=None if args.dynamic < 0 else bool(args.dynamic), scan_rows=None if args.scan_rows < 0 else args.scan_rows)
     pool.fold_all(msas[:k], None, 10, 100, host_threads=bool(args.host_threads))                       # warm-up: workspaces, tensor maps, module load
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -69,7 +69,7 @@ for k in [int(x) for x in args.streams.split(',')]:
     ok = all(bool(torch.isfinite(c).all()) for c, _ in res)
     if rank == 0:
         print(json.dumps({'workload': '%d targets L=%d N=%d, 10 iter + 100 min-steps' % (args.targets, args.L, args.N), 'gpus': world,
-                          'streams_per_gpu': k, 'conv_sms': args.conv_sms, 'conv_dynamic': pool.conv_dynamic, 'host_threads': bool(args.host_threads), 'scan_rows': args.scan_rows, 'conv_mode': args.conv_mode, 'batch_ms': ms,
+                          'streams_per_gpu': k, 'conv_sms': args.conv_sms, 'conv_dynamic': pool.conv_dynamic, 'host_threads': bool(args.host_threads), 'scan_rows': pool.scan_rows, 'conv_mode': args.conv_mode, 'batch_ms': ms,
                           'ms_per_target': ms / args.targets, 'targets_per_s': args.targets / ms * 1e3, 'finite': ok}), flush=True)
     pool.close()
 if world > 1:
