@@ -52,6 +52,19 @@ def test_stream_pool_host_logic():
     assert all(e.closed for e in engines) and pool.engines == []
     with pytest.raises(ValueError):
         P.StreamPool(streams=0, engine_factory=Fake)
+    # defaults: shared vgru scans (and the dynamic conv schedule) only when several streams share the GPU; the graph
+    # option reaches every engine that has one
+    assert P.StreamPool(streams=1, engine_factory=Fake).scan_rows == 0 and pool.scan_rows == 384
+    assert P.StreamPool(streams=1, scan_rows=256, engine_factory=Fake).scan_rows == 256
+    assert P.StreamPool(streams=1, engine_factory=Fake).conv_dynamic is False and P.StreamPool(streams=2, engine_factory=Fake).conv_dynamic is True
+
+    class FakeG(Fake):
+        graph = None
+
+        def set_graph(self, on):
+            self.graph = on
+    assert [e.graph for e in P.StreamPool(streams=2, graph=True, engine_factory=FakeG).engines] == [True, True]
+    assert [e.graph for e in P.StreamPool(streams=2, engine_factory=FakeG).engines] == [None, None]
 
 
 def _free_port():
