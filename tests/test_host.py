@@ -2,6 +2,7 @@
 import ctypes
 import os
 import re
+import subprocess
 
 import numpy as np
 import pytest
@@ -26,6 +27,29 @@ def test_library_builds_and_exports_every_declared_symbol():
         assert hasattr(lib, name), f'{name} declared in include/dmp2.h but not exported'
     from dmpfold2_b200 import engine
     assert declared == set(engine.EXPORTS)            # the ctypes binding types every export
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/dmp2.h is a C header (strict C99, no C++/torch types): a plain-C program includes it, links against
+    libdmp2.so and runs the host-only entry points (tests/c_abi_consumer.c)."""
+    lib_path = _build()
+    exe = str(tmp_path / 'c_abi_consumer')
+    libdir = os.path.dirname(lib_path)
+    r = subprocess.run(['gcc', '-std=c99', '-pedantic', '-Wall', '-Wextra', '-Werror', '-I', os.path.join(ROOT, 'include'),
+                        os.path.join(ROOT, 'tests', 'c_abi_consumer.c'), '-o', exe, '-L', libdir, '-l:libdmp2.so',
+                        '-Wl,-rpath,' + libdir, '-Wl,--allow-shlib-undefined'], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    env = dict(os.environ)
+    paths = ['/usr/local/cuda/lib64', env.get('LD_LIBRARY_PATH', '')]
+    try:                                              # the CUDA runtime the venv ships (what ctypes/torch resolve to)
+        import nvidia.cuda_runtime
+        paths.insert(0, os.path.join(list(nvidia.cuda_runtime.__path__)[0], 'lib'))
+    except ImportError:
+        pass
+    env['LD_LIBRARY_PATH'] = os.pathsep.join(p for p in paths if p)
+    out = subprocess.run([exe], capture_output=True, text=True, env=env)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert 'all ok' in out.stdout and 'strip_rows: ok' in out.stdout
 
 
 def test_create_without_gpu_fails_loudly():
